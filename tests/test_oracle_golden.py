@@ -1,0 +1,70 @@
+"""Pin the oracle: it must reproduce the reference's own outputs (tests/golden/, minted by
+oracle/gen_golden.py from the unmodified reference) before anything is compared against it."""
+import pytest
+import torch
+
+from oracle import superglue_oracle as O
+from conftest import GOLDEN_FULL, GOLDEN_SAMPLED
+
+
+@pytest.mark.parametrize('name', GOLDEN_FULL)
+def test_oracle_matches_reference_full(golden, name):
+    fx = golden(name)
+    out = O.run(fx['state_dict'], fx['config'], fx['data'], fx['match_threshold'])
+    # same ATen ops, same order => fp32 agreement to rounding noise
+    assert (out['scores'] - fx['scores_f32']).abs().max() <= 2e-6
+    assert (out['context_descriptors0'] - fx['context_descriptors0_f32']).abs().max() <= 1e-5
+    assert (out['context_descriptors1'] - fx['context_descriptors1_f32']).abs().max() <= 1e-5
+    assert torch.equal(out['matches0'], fx['matches0'])
+    assert (out['matching_scores0'] - fx['matching_scores0']).abs().max() <= 2e-6
+    # fp64 oracle vs fp64 reference
+    out64 = O.run(fx['state_dict'], fx['config'], fx['data'], fx['match_threshold'], dtype=torch.float64)
+    assert (out64['scores'] - fx['scores_f64']).abs().max() <= 1e-10
+
+
+@pytest.mark.parametrize('name', GOLDEN_SAMPLED)
+def test_oracle_matches_reference_c1(golden, name):
+    """BASELINE.json configs[0]: 1 pair, N=M=512, d=256, 9 stages, 20 Sinkhorn iterations."""
+    fx = golden(name)
+    out = O.run(fx['state_dict'], fx['config'], fx['data'], fx['match_threshold'])
+    s = out['scores']
+    assert (s[:, ::7, ::5] - fx['scores_f32_sample']).abs().max() <= 5e-6
+    assert (s[:, -1, :] - fx['scores_f32_lastrow']).abs().max() <= 5e-6
+    assert (s[:, :, -1] - fx['scores_f32_lastcol']).abs().max() <= 5e-6
+    assert (out['context_descriptors0'][:, ::4, ::8] - fx['ctx0_f32_sample']).abs().max() <= 2e-5
+    assert torch.equal(out['matches0'], fx['matches0'])
+    assert (out['matching_scores0'] - fx['matching_scores0']).abs().max() <= 5e-6
+    rel = (s.double().sum(2) - fx['scores_f64_rowsum']).abs().max() / fx['scores_f64_rowsum'].abs().max()
+    assert rel < 1e-6
+
+
+def test_planted_matches_are_recovered(golden):
+    fx = golden('C1_planted')
+    planted = fx['data']['planted_matches0']
+    m0 = fx['matches0']
+    has = planted >= 0
+    assert has.sum() >= 300
+    assert torch.equal(m0[has], planted[has])              # every planted pair is recovered
+
+
+def test_sinkhorn_marginals():
+    """Property of the algorithm (optimal_transport.py:20-28): after the v update the column
+    marginals of exp(Z+u+v) equal b exactly, the row marginals approximately."""
+    torch.manual_seed(0)
+    s = torch.randn(2, 30, 41, dtype=torch.float64) * 3
+    lp = O.matching_log_probs(s, torch.tensor(1.0, dtype=torch.float64), 200, 1.0)
+    m, n = 30, 41
+    p = (lp + (-torch.log(torch.tensor(float(m + n))))).exp()
+    col = p.sum(1)
+    assert torch.allclose(col[:, :-1], torch.full((2, n), 1.0 / (m + n), dtype=torch.float64), atol=1e-12)
+    assert torch.allclose(col[:, -1], torch.full((2,), m / (m + n), dtype=torch.float64), atol=1e-12)
+    assert torch.allclose(p.sum(2)[:, :-1], torch.full((2, m), 1.0 / (m + n), dtype=torch.float64), atol=1e-6)
+
+
+def test_extract_matches_ties_first_index():
+    s = torch.full((1, 4, 4), -5.0)
+    s[0, 0, 1] = s[0, 0, 2] = -0.1          # row tie -> first index (1)
+    s[0, 1, 1] = -0.2
+    out = O.extract_matches(s, 0.2)
+    assert out['matches0'][0, 0].item() == 1
+    assert out['matches0'][0, 1].item() == -1      # column 1's best row is 0, not mutual
