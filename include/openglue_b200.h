@@ -1,0 +1,179 @@
+/*
+ * openglue_b200.h  --  C ABI of libopenglue_b200.so
+ *
+ * A B200 (sm_100a) implementation of ONE path of ucuapps/OpenGlue: the SuperGlue-style
+ * matching core (reference models/superglue/*, models/matching_module.py:149-187).
+ * The reference is pure Python and has no FFI; these entry points are what a binding for
+ * this path binds (ctypes today).  Each function names the reference
+ * code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory unless the name ends in
+ *     `_host`; nothing is allocated, freed or synchronised behind the caller's back;
+ *   - every call enqueues work on `stream` and returns immediately;
+ *   - return value: OG_OK (0) or a negative og_status; og_last_error() gives a
+ *     thread-local message for the last failure on the calling thread;
+ *   - activations are keypoint-major: row = keypoint, `d` channels contiguous.  The
+ *     reference's channel-first [B, d, n] tensors appear only at the Python-visible
+ *     outputs (context descriptors);
+ *   - all floating-point data is IEEE fp32; match indices are int64 (torch.int64).
+ */
+#ifndef OPENGLUE_B200_H_
+#define OPENGLUE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OG_VERSION 100          /* major*10000 + minor*100 + patch */
+
+typedef enum og_status {
+  OG_OK = 0,
+  OG_EINVAL = -1,               /* bad argument (null pointer, non-positive size, misalignment) */
+  OG_EUNSUPPORTED = -2,         /* shape / option outside what the kernels cover               */
+  OG_ECUDA = -3,                /* a CUDA runtime call failed (message has the CUDA error)      */
+  OG_EWORKSPACE = -4            /* workspace too small                                          */
+} og_status;
+
+/* arithmetic of the GEMM-shaped contractions */
+typedef enum og_precision {
+  OG_PREC_FP32 = 0,             /* CUDA-core FFMA, fp32 accumulate: the exact mode                 */
+  OG_PREC_TF32X3 = 1            /* tcgen05 kind::tf32, hi/lo operand split, 3 products, fp32 accum  */
+} og_precision;
+
+#define OG_MAX_HIDDEN 8
+
+/* Mirrors the reference's nested config dict (models/superglue/superglue.py:12-27). */
+typedef struct og_config {
+  int32_t descriptor_dim;       /* d;  config['descriptor_dim']                                  */
+  int32_t num_heads;            /* H;  attention_gnn.num_heads, heads = contiguous channel blocks */
+  int32_t num_layers;           /* 2 * attention_gnn.num_stages (even = self, odd = cross)        */
+  int32_t side_info_size;       /* S;  positional_encoding.side_info_size                          */
+  int32_t num_hidden;           /* len(positional_encoding.hidden_layers_sizes)                    */
+  int32_t hidden[OG_MAX_HIDDEN];
+  int32_t sinkhorn_iters;       /* otp.num_iters                                                   */
+  float   sinkhorn_reg;         /* otp.reg                                                         */
+  float   match_threshold;      /* inference.match_threshold (config/config.yaml:40)               */
+  int32_t precision;            /* og_precision                                                    */
+} og_config;
+
+int         og_version(void);
+const char* og_last_error(void);
+/* Number of SMs / compute capability of the current device (capability cache, read-only). */
+int         og_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed weights.  The host side folds eval-mode BatchNorm forward into the following conv
+ * (reference models/utils.py:48-58: Conv -> ReLU -> BN), folds `out_proj` into `fc.0`
+ * (attention_gnn.py:32,52-55) and sigmoid(mix_coefs) into `linear_proj` (superglue.py:58-62),
+ * in float64, and lays the result out as one flat fp32 buffer:
+ *
+ *   kenc:   for i in 0..num_hidden:  W_i [out_i, in_i],  b_i [out_i]      (in_0 = 2 + S)
+ *   layer l (0..num_layers-1):  Wqkv [3d, d], bqkv [3d], W1 [2d, 2d], b1 [2d], W2 [d, 2d], b2 [d]
+ *   final:  Wp [d, d], bp [d], rmix [d]   (rmix = 1 - sigmoid(mix_coefs), zeros without residual)
+ *   dustbin_score [1]
+ *
+ * og_packed_offset() returns the float offset of a tensor inside that buffer.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum og_tensor_id {
+  OG_T_KENC_W = 0, OG_T_KENC_B = 1,               /* index = kenc linear layer 0..num_hidden     */
+  OG_T_QKV_W = 2, OG_T_QKV_B = 3, OG_T_FC1_W = 4, OG_T_FC1_B = 5, OG_T_FC2_W = 6, OG_T_FC2_B = 7,
+                                                  /* index = GNN layer                           */
+  OG_T_PROJ_W = 8, OG_T_PROJ_B = 9, OG_T_PROJ_RMIX = 10, OG_T_DUSTBIN = 11   /* index ignored    */
+} og_tensor_id;
+
+int64_t og_packed_weight_floats(const og_config* cfg);
+int64_t og_packed_offset(const og_config* cfg, int tensor_id, int index);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole path.  Replaces SuperGlue.forward (models/superglue/superglue.py:29-72) plus the
+ * match extraction of MatchingTrainingModule.forward (models/matching_module.py:174-187) and
+ * its reverse direction (inference.py:176-190).
+ *
+ *   kpts{0,1}  [B, n|m, 2] pixel (x, y);  side{0,1} [B, n|m, S];  desc{0,1} [B, n|m, d]
+ *   img_wh     host array {W0, H0, W1, H1}  (superglue.py:35-41, 74-78)
+ *   ctx{0,1}   [B, d, n|m]  channel-first context descriptors   (may be NULL)
+ *   scores     [B, n+1, m+1] log assignment incl. dustbins
+ *   matches0   [B, n] int64 (-1 = no match), mscores0 [B, n];  matches1/mscores1 [B, m] (may be NULL)
+ *   workspace  >= og_workspace_bytes(cfg, B, n, m), 256-byte aligned
+ * ------------------------------------------------------------------------------------------- */
+int64_t og_workspace_bytes(const og_config* cfg, int batch, int n, int m);
+
+int og_superglue_forward(const og_config* cfg, const float* packed_weights,
+                         int batch, int n, int m,
+                         const float* kpts0, const float* kpts1,
+                         const float* side0, const float* side1,
+                         const float* desc0, const float* desc1,
+                         const float* img_wh_host,
+                         float* ctx0, float* ctx1, float* scores,
+                         int64_t* matches0, float* mscores0,
+                         int64_t* matches1, float* mscores1,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Number of kernel launches the last og_superglue_forward on this thread enqueued. */
+int og_last_forward_launches(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Operator-level entry points (what the whole-path call is built from; tested one by one
+ * against the matching oracle function).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Y = epilogue( alpha * [A | A2] . W^T + bias ).   Replaces every Conv1d(k=1) of the path
+ * (attention_gnn.py:16-20,24-26,32; models/utils.py:53-57; superglue.py:58) and, batched,
+ * calculate_matching_score (superglue.py:80-86).
+ *   A  [batch][rows, k1] (lda, strideA)   A2 [batch][rows, k2] or NULL (concat along K)
+ *   W  [nout, k1+k2] (ldw; strideW != 0 => one W per batch item)     bias [nout] or NULL
+ *   relu: clamp at 0 after bias.   R/rscale: Y += rscale[o] * R[r, o]  (rscale NULL => 1)
+ *   Y  [rows, nout] (ldy) and/or Yt [nout, rows] (ldyt) - either may be NULL              */
+typedef struct og_linear_args {
+  const float* A;  int64_t lda;  int64_t strideA;
+  const float* A2; int64_t lda2; int64_t strideA2;
+  int32_t k1, k2;
+  const float* W;  int64_t ldw;  int64_t strideW;
+  const float* bias;
+  int32_t rows, nout, batch;
+  float   alpha;
+  int32_t relu;
+  const float* R;  int64_t ldr;  int64_t strideR;
+  const float* rscale;
+  float* Y;  int64_t ldy;  int64_t strideY;
+  float* Yt; int64_t ldyt; int64_t strideYt;
+} og_linear_args;
+int og_linear_fwd(const og_linear_args* args, int precision, void* stream);
+
+/* out[b, i, h*Dh + c] = sum_j softmax_j(q_i . k_j * Dh^-0.5) v_j[c]  per head h.
+ * Replaces softmax_attention (models/superglue/attention.py:8-19) inside
+ * MultiheadAttention.forward (attention_gnn.py:22-32); the N x M probabilities are never
+ * materialised.  q [batch][nq, *] row stride ldq; k, v [batch][nk, *]; heads are contiguous
+ * channel blocks of width Dh = d / H.                                                        */
+int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq,
+                     const float* k, int64_t ldk, int64_t stridek,
+                     const float* v, int64_t ldv, int64_t stridev,
+                     float* out, int64_t ldo, int64_t strideo,
+                     int batch, int nq, int nk, int num_heads, int head_dim,
+                     int precision, void* stream);
+
+/* Dustbin-augmented log-domain Sinkhorn.  Replaces SuperGlue.get_matching_probs
+ * (superglue.py:88-111) + log_otp_solver (optimal_transport.py:4-28).
+ *   S       [B][n, lds]  inner score block (lds >= m, multiple of 4, 16-byte aligned rows)
+ *   dustbin device scalar;   scores [B, n+1, m+1]
+ *   workspace >= og_sinkhorn_workspace_bytes(B, n, m)                                          */
+int64_t og_sinkhorn_workspace_bytes(int batch, int n, int m);
+int og_sinkhorn_fwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin,
+                    int batch, int n, int m, int iters, float reg,
+                    float* scores, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Mutual-argmax match extraction on scores[:, :n, :m].  Replaces
+ * models/matching_module.py:174-187 and inference.py:176-190 (ties -> lowest index).
+ *   workspace >= og_match_workspace_bytes(B, n, m)                                             */
+int64_t og_match_workspace_bytes(int batch, int n, int m);
+int og_match_fwd(const float* scores, int batch, int n, int m, float threshold,
+                 int64_t* matches0, float* mscores0, int64_t* matches1, float* mscores1,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* OPENGLUE_B200_H_ */

@@ -1,0 +1,112 @@
+"""ctypes binding of libopenglue_b200.so (include/openglue_b200.h).
+
+The library is the product: there is NO Python/torch fallback for any kernel.  If the shared
+object is missing or a call fails, this module raises - loudly - instead of computing the
+result some other way.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libopenglue_b200.so')
+
+OG_OK = 0
+OG_PREC_FP32, OG_PREC_TF32X3 = 0, 1
+OG_MAX_HIDDEN = 8
+(OG_T_KENC_W, OG_T_KENC_B, OG_T_QKV_W, OG_T_QKV_B, OG_T_FC1_W, OG_T_FC1_B, OG_T_FC2_W, OG_T_FC2_B,
+ OG_T_PROJ_W, OG_T_PROJ_B, OG_T_PROJ_RMIX, OG_T_DUSTBIN) = range(12)
+
+
+class OgConfig(C.Structure):
+    _fields_ = [('descriptor_dim', C.c_int32), ('num_heads', C.c_int32), ('num_layers', C.c_int32),
+                ('side_info_size', C.c_int32), ('num_hidden', C.c_int32), ('hidden', C.c_int32 * OG_MAX_HIDDEN),
+                ('sinkhorn_iters', C.c_int32), ('sinkhorn_reg', C.c_float), ('match_threshold', C.c_float),
+                ('precision', C.c_int32)]
+
+
+class OgLinearArgs(C.Structure):
+    _fields_ = [('A', C.c_void_p), ('lda', C.c_int64), ('strideA', C.c_int64),
+                ('A2', C.c_void_p), ('lda2', C.c_int64), ('strideA2', C.c_int64),
+                ('k1', C.c_int32), ('k2', C.c_int32),
+                ('W', C.c_void_p), ('ldw', C.c_int64), ('strideW', C.c_int64),
+                ('bias', C.c_void_p),
+                ('rows', C.c_int32), ('nout', C.c_int32), ('batch', C.c_int32),
+                ('alpha', C.c_float), ('relu', C.c_int32),
+                ('R', C.c_void_p), ('ldr', C.c_int64), ('strideR', C.c_int64),
+                ('rscale', C.c_void_p),
+                ('Y', C.c_void_p), ('ldy', C.c_int64), ('strideY', C.c_int64),
+                ('Yt', C.c_void_p), ('ldyt', C.c_int64), ('strideYt', C.c_int64)]
+
+
+# every symbol include/openglue_b200.h declares: (restype, argtypes)
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_CFG = C.POINTER(OgConfig)
+SYMBOLS = {
+    'og_version': (_I, []),
+    'og_last_error': (C.c_char_p, []),
+    'og_device_info': (_I, [C.POINTER(C.c_int)] * 3),
+    'og_packed_weight_floats': (_L, [_CFG]),
+    'og_packed_offset': (_L, [_CFG, _I, _I]),
+    'og_workspace_bytes': (_L, [_CFG, _I, _I, _I]),
+    'og_superglue_forward': (_I, [_CFG, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float),
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    'og_last_forward_launches': (_I, []),
+    'og_linear_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P]),
+    'og_attention_fwd': (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
+    'og_sinkhorn_workspace_bytes': (_L, [_I, _I, _I]),
+    'og_sinkhorn_fwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _L, _P]),
+    'og_match_workspace_bytes': (_L, [_I, _I, _I]),
+    'og_match_fwd': (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class OpenGlueB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OpenGlueB200Error(
+                f'{LIB_PATH} is missing: build it with `python -m openglue_b200.build` '
+                '(there is no fallback implementation)')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OG_OK:
+        msg = lib().og_last_error()
+        raise OpenGlueB200Error(f'{what} failed with status {rc}: {msg.decode() if msg else "?"}')
+
+
+def make_config(config: dict, match_threshold: float = 0.2, precision: int = OG_PREC_FP32) -> OgConfig:
+    """Translate the reference's nested config dict (superglue.py:12-27) to og_config."""
+    pe, gnn = config['positional_encoding'], config['attention_gnn']
+    hidden = list(pe.get('hidden_layers_sizes') or [])
+    if len(hidden) > OG_MAX_HIDDEN:
+        raise ValueError(f'at most {OG_MAX_HIDDEN} hidden layers in the positional encoder')
+    c = OgConfig()
+    c.descriptor_dim = int(config['descriptor_dim'])
+    c.num_heads = int(gnn['num_heads'])
+    c.num_layers = 2 * int(gnn['num_stages'])
+    c.side_info_size = int(pe.get('side_info_size', 1))
+    c.num_hidden = len(hidden)
+    for i, h in enumerate(hidden):
+        c.hidden[i] = int(h)
+    c.sinkhorn_iters = int(config['otp']['num_iters'])
+    c.sinkhorn_reg = float(config['otp']['reg'])
+    c.match_threshold = float(match_threshold)
+    c.precision = int(precision)
+    return c

@@ -1,0 +1,59 @@
+// Shared helpers for the openglue_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/openglue_b200.h"
+
+namespace og {
+
+// thread-local error message (og_last_error)
+inline char* err_buf() { static thread_local char buf[512] = {0}; return buf; }
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(err_buf(), 512, fmt, ap); va_end(ap);
+  return code;
+}
+#define OG_CHECK_ARG(cond, ...) do { if (!(cond)) return og::fail(OG_EINVAL, __VA_ARGS__); } while (0)
+#define OG_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return og::fail(OG_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define OG_LAUNCH_CHECK(name) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+  return og::fail(OG_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); } while (0)
+
+inline int& launch_counter() { static thread_local int c = 0; return c; }
+
+struct DeviceInfo { int sm_count = 0, cc_major = 0, cc_minor = 0; bool ok = false; };
+inline const DeviceInfo& device_info() {
+  // immutable per-process capability cache (first use wins; one device per process by design)
+  static DeviceInfo info = [] {
+    DeviceInfo d; int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return d;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return d;
+    d.sm_count = p.multiProcessorCount; d.cc_major = p.major; d.cc_minor = p.minor; d.ok = true;
+    return d;
+  }();
+  return info;
+}
+
+__host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+}  // namespace og

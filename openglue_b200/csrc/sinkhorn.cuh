@@ -1,0 +1,294 @@
+// Dustbin-augmented log-domain Sinkhorn, all iterations in ONE persistent cooperative launch.
+// Replaces SuperGlue.get_matching_probs (superglue.py:88-111) + log_otp_solver
+// (optimal_transport.py:4-28).
+//
+// Formulation (algebraically the reference's iteration, one sweep + one exp per element):
+//   row i:      t_ij = z_ij + v_j,  mx_i = max_j t_ij,  e_ij = exp(t_ij - mx_i),  S_i = sum_j e_ij
+//               u_i  = log_a_i - (mx_i + log S_i)                     [= log_a - LSE_j(Z + v)]
+//   column j:   exp(z_ij + u_i) = e_ij * (a_i / S_i) * exp(-v_j)  =>
+//               c_j = sum_i e_ij * a_i / S_i ,   v_j <- log_b_j + v_j - log c_j
+//                                                                     [= log_b - LSE_i(Z + u)]
+// so a row is read once per iteration, kept in registers between its row reduction and its
+// column contribution, and the augmented (n+1) x (m+1) matrix is never materialised: the
+// dustbin row and column are the constant dustbin score and are generated in registers.
+//
+// Decomposition: pair b is cut into SP strips of whole rows, one CTA per strip, one warp per
+// row (float4 per lane, V float4s per lane => m <= 128 V).  Column sums are reduced
+// warp -> CTA (shared memory) -> grid (per-strip partials in global memory, double buffered),
+// with one grid-wide barrier per iteration; every CTA of a pair then rebuilds v redundantly
+// in a fixed order (deterministic, no atomics on data).
+#pragma once
+#include "common.cuh"
+#include <math_constants.h>
+#include <algorithm>
+
+namespace og {
+
+struct SinkArgs {
+  const float* S; int64_t lds, strideS;
+  const float* dustbin;
+  int B, n, m, iters;
+  float reg;
+  float norm, log_a_last, log_b_last;   // -log(n+m), norm + log(m), norm + log(n)   (superglue.py:98-101)
+  float* scores;                         // [B, n+1, m+1]
+  float* u;                              // [B, n+1]   workspace
+  float* partial;                        // [2, B, SP, mpad] workspace
+  unsigned int* barrier;                 // zeroed before launch
+  int SP, rows_per_strip, mpad;
+};
+
+constexpr int SINK_WARPS = 8;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int V>
+__global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a) {
+  extern __shared__ __align__(16) float og_sink_smem[];
+  float* v_s = og_sink_smem;                         // [mpad]   v_j, j = 0..m (m = dustbin column)
+  float* red = og_sink_smem + a.mpad;                // [SINK_WARPS][mpad]
+  const int b = blockIdx.x / a.SP, strip = blockIdx.x % a.SP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = a.n, m = a.m;
+  const int r0 = strip * a.rows_per_strip;
+  const int r1 = min(r0 + a.rows_per_strip, n + 1);
+  const float* __restrict__ Sb = a.S + (int64_t)b * a.strideS;
+  const bool unit_reg = (a.reg == 1.0f);
+  const float dz = unit_reg ? __ldg(a.dustbin) : __fdiv_rn(__ldg(a.dustbin), a.reg);   // Z = M / reg
+  const float a_reg = expf(a.norm), a_last = expf(a.log_a_last);
+
+  for (int j = tid; j <= m; j += blockDim.x) v_s[j] = 0.f;
+  __syncthreads();
+
+  auto load_row = [&](int row, float4 (&z)[V]) {
+    if (row < n) {
+      const float4* src = reinterpret_cast<const float4*>(Sb + (int64_t)row * a.lds);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int idx = lane + 32 * k;
+        z[k] = (4 * idx < m) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  auto scale_row = [&](int row, float4 (&z)[V]) {     // Z = M / reg; the dustbin row is constant
+    if (row >= n) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) z[k] = make_float4(dz, dz, dz, dz);
+    } else if (!unit_reg) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
+        z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
+      }
+    }
+  };
+
+  for (int it = 0; it < a.iters; ++it) {
+    float4 cacc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cacc_m = 0.f;
+    const float v_m = v_s[m];
+
+    float4 z[V], zn[V];
+    int row = r0 + warp;
+    if (row < r1) load_row(row, z);
+    for (; row < r1; row += SINK_WARPS) {
+      const int nxt = row + SINK_WARPS;
+      if (nxt < r1) load_row(nxt, zn);               // prefetch: next row's loads fly during this row's math
+      scale_row(row, z);
+      // t = z + v, masked; row max
+      const float t_m = dz + v_m;                    // dustbin column entry of this row
+      float mx = t_m;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        const float4 vv = *reinterpret_cast<const float4*>(v_s + c);   // c < mpad always
+        z[k].x = (c + 0 < m) ? z[k].x + vv.x : -CUDART_INF_F;
+        z[k].y = (c + 1 < m) ? z[k].y + vv.y : -CUDART_INF_F;
+        z[k].z = (c + 2 < m) ? z[k].z + vv.z : -CUDART_INF_F;
+        z[k].w = (c + 3 < m) ? z[k].w + vv.w : -CUDART_INF_F;
+        mx = fmaxf(mx, fmaxf(fmaxf(z[k].x, z[k].y), fmaxf(z[k].z, z[k].w)));
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        z[k].x = ex2_approx((z[k].x - mx) * LOG2E_F);
+        z[k].y = ex2_approx((z[k].y - mx) * LOG2E_F);
+        z[k].z = ex2_approx((z[k].z - mx) * LOG2E_F);
+        z[k].w = ex2_approx((z[k].w - mx) * LOG2E_F);
+        sum += (z[k].x + z[k].y) + (z[k].z + z[k].w);
+      }
+      const float e_m = ex2_approx((t_m - mx) * LOG2E_F);
+      const float s_i = warp_sum(sum) + e_m;
+      const float w_i = __fdiv_rn((row < n) ? a_reg : a_last, s_i);
+      if (it == a.iters - 1 && lane == 0)
+        a.u[(int64_t)b * (n + 1) + row] = ((row < n) ? a.norm : a.log_a_last) - (mx + logf(s_i));
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        cacc[k].x = fmaf(z[k].x, w_i, cacc[k].x); cacc[k].y = fmaf(z[k].y, w_i, cacc[k].y);
+        cacc[k].z = fmaf(z[k].z, w_i, cacc[k].z); cacc[k].w = fmaf(z[k].w, w_i, cacc[k].w);
+      }
+      cacc_m = fmaf(e_m, w_i, cacc_m);
+#pragma unroll
+      for (int k = 0; k < V; ++k) z[k] = zn[k];
+    }
+    // warp -> CTA
+    float* myred = red + warp * a.mpad;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < m) *reinterpret_cast<float4*>(myred + c) = cacc[k];       // entries >= m are zero
+    }
+    __syncthreads();                                  // (a) all float4 column sums are in `red`
+    if (lane == 0) myred[m] = cacc_m;                 // column m = dustbin column (may overlap a float4 tail)
+    __syncthreads();
+    float* part = a.partial + ((int64_t)(it & 1) * a.B * a.SP + (int64_t)b * a.SP + strip) * a.mpad;
+    for (int j = tid; j <= m; j += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < SINK_WARPS; ++w) s += red[w * a.mpad + j];
+      part[j] = s;
+    }
+    grid_barrier(a.barrier, (unsigned int)(it + 1) * gridDim.x);
+    // every CTA of the pair rebuilds v (fixed summation order => bitwise identical across CTAs)
+    const float* pb = a.partial + ((int64_t)(it & 1) * a.B * a.SP + (int64_t)b * a.SP) * a.mpad;
+    for (int j = tid; j <= m; j += blockDim.x) {
+      float c = 0.f;
+      for (int s = 0; s < a.SP; ++s) c += __ldcg(pb + (int64_t)s * a.mpad + j);
+      const float log_b = (j < m) ? a.norm : a.log_b_last;
+      v_s[j] = log_b + v_s[j] - logf(c);
+    }
+    __syncthreads();
+  }
+
+  // final pass: scores = Z + u + v - norm   (optimal_transport.py:28, superglue.py:111)
+  {
+    const float v_m = v_s[m];
+    float4 z[V];
+    for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
+      load_row(row, z);
+      scale_row(row, z);
+      float u_i = 0.f;
+      if (a.iters > 0) {
+        if (lane == 0) u_i = a.u[(int64_t)b * (n + 1) + row];
+        u_i = __shfl_sync(0xffffffffu, u_i, 0);
+      }
+      float* out = a.scores + ((int64_t)b * (n + 1) + row) * (m + 1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        if (c < m) {
+          const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
+          if (c + 0 < m) out[c + 0] = (z[k].x + u_i) + vv.x - a.norm;
+          if (c + 1 < m) out[c + 1] = (z[k].y + u_i) + vv.y - a.norm;
+          if (c + 2 < m) out[c + 2] = (z[k].z + u_i) + vv.z - a.norm;
+          if (c + 3 < m) out[c + 3] = (z[k].w + u_i) + vv.w - a.norm;
+        }
+      }
+      if (lane == 0) out[m] = (dz + u_i) + v_m - a.norm;
+    }
+  }
+}
+
+struct SinkPlan { int V, SP, rows_per_strip, mpad, pairs_per_launch; size_t smem; };
+
+inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
+  if (m <= 512) p->V = 4; else if (m <= 1024) p->V = 8; else if (m <= 2048) p->V = 16;
+  else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > 2048 columns not supported (swap the images)", m);
+  const int sms = device_info().ok ? device_info().sm_count : 148;
+  p->pairs_per_launch = B < sms ? B : sms;
+  int sp = sms / p->pairs_per_launch;
+  if (sp > 16) sp = 16;
+  const int max_sp = cdiv(n + 1, SINK_WARPS);
+  if (sp > max_sp) sp = max_sp;
+  if (sp < 1) sp = 1;
+  p->SP = sp;
+  p->rows_per_strip = cdiv(n + 1, sp);
+  p->mpad = (int)align_up(m + 1, 4);
+  if (p->mpad < 128 * p->V) {                      // v_s is read as float4 up to column 128 V - 1
+    // only columns < m are ever used, but the smem reads must stay in bounds
+  }
+  p->smem = (size_t)(1 + SINK_WARPS) * (size_t)std::max(p->mpad, 128 * p->V) * sizeof(float);
+  return OG_OK;
+}
+
+inline int64_t sinkhorn_workspace_bytes(int B, int n, int m) {
+  SinkPlan p;
+  if (sinkhorn_plan(B, n, m, &p) != OG_OK) return -1;
+  const int64_t mp = std::max(p.mpad, 128 * p.V);
+  return align_up(256, 256) + align_up((int64_t)B * (n + 1) * 4, 256) + align_up(2LL * B * p.SP * mp * 4, 256);
+}
+
+template <int V>
+inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.B * a.SP);
+  cfg.blockDim = dim3(SINK_WARPS * 32);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  OG_CUDA(cudaLaunchKernelEx(&cfg, sinkhorn_kernel<V>, a));
+  launch_counter()++;
+  return OG_OK;
+}
+
+inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const float* dustbin, int B, int n, int m,
+                           int iters, float reg, float* scores, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+  SinkPlan p;
+  int rc = sinkhorn_plan(B, n, m, &p);
+  if (rc != OG_OK) return rc;
+  if (ws_bytes < sinkhorn_workspace_bytes(B, n, m)) return fail(OG_EWORKSPACE, "sinkhorn: workspace too small");
+  if (lds % 4 != 0 || lds < m || (reinterpret_cast<uintptr_t>(S) & 15) || strideS % 4 != 0)
+    return fail(OG_EINVAL, "sinkhorn: S rows must be 16-byte aligned (lds %% 4 == 0, lds >= m)");
+  const int64_t mp = std::max(p.mpad, 128 * p.V);
+  char* w = static_cast<char*>(ws);
+  unsigned int* barrier = reinterpret_cast<unsigned int*>(w); w += 256;
+  float* u = reinterpret_cast<float*>(w); w += align_up((int64_t)B * (n + 1) * 4, 256);
+  float* partial = reinterpret_cast<float*>(w);
+  // host-side constants exactly as the reference builds them (float32 throughout)
+  const float norm = -logf((float)(n + m));
+  const float log_a_last = norm + (float)log((double)m);     // log_a[-1] += math.log(n_cols)
+  const float log_b_last = norm + (float)log((double)n);     // log_b[-1] += math.log(n_rows)
+  for (int b0 = 0; b0 < B; b0 += p.pairs_per_launch) {
+    const int nb = std::min(p.pairs_per_launch, B - b0);
+    SinkArgs a;
+    a.S = S + (int64_t)b0 * strideS; a.lds = lds; a.strideS = strideS; a.dustbin = dustbin;
+    a.B = nb; a.n = n; a.m = m; a.iters = iters; a.reg = reg;
+    a.norm = norm; a.log_a_last = log_a_last; a.log_b_last = log_b_last;
+    a.scores = scores + (int64_t)b0 * (n + 1) * (m + 1);
+    a.u = u; a.partial = partial; a.barrier = barrier;
+    a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = (int)mp;
+    OG_CUDA(cudaMemsetAsync(barrier, 0, 256, stream));
+    switch (p.V) {
+      case 4:  rc = sinkhorn_launch_v<4>(a, p, stream); break;
+      case 8:  rc = sinkhorn_launch_v<8>(a, p, stream); break;
+      default: rc = sinkhorn_launch_v<16>(a, p, stream); break;
+    }
+    if (rc != OG_OK) return rc;
+  }
+  return OG_OK;
+}
+
+}  // namespace og

@@ -1,0 +1,236 @@
+"""Drop-in replacement for the reference's ``models.superglue.superglue.SuperGlue``.
+
+Same constructor config, same ``state_dict`` keys and shapes (so reference checkpoints load,
+reference inference.py:71-75) and the same ``forward(data) -> dict`` contract
+(reference superglue.py:29-72); the arithmetic runs in libopenglue_b200.so (hand-written
+sm_100a CUDA behind a C ABI, include/openglue_b200.h).  ``MatchingCore`` adds the match
+extraction of ``MatchingTrainingModule.forward`` (reference models/matching_module.py:149-187).
+
+There is no CPU or PyTorch fallback for the kernels: a missing library or a non-CUDA
+device is an error, not a slow path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .packing import pack_weights
+
+__all__ = ['SuperGlue', 'MatchingCore']
+
+
+def _feed_forward_params(*sizes: int) -> nn.Sequential:
+    """Parameter container with the reference FeedForwardNet's key layout (models/utils.py:48-58):
+    index 3i = Conv1d(k=1), 3i+1 = ReLU, 3i+2 = BatchNorm1d, last = Conv1d.  Never called."""
+    layers = []
+    for i in range(1, len(sizes) - 1):
+        layers += [nn.Conv1d(sizes[i - 1], sizes[i], kernel_size=1), nn.ReLU(inplace=True), nn.BatchNorm1d(sizes[i])]
+    layers.append(nn.Conv1d(sizes[-2], sizes[-1], kernel_size=1))
+    return nn.Sequential(*layers)
+
+
+class _Holder(nn.Module):
+    """Plain namespace module (keeps state_dict prefixes identical to the reference's)."""
+
+
+def _gnn_params(num_stages: int, d: int) -> nn.Module:
+    gnn = _Holder()
+    gnn.layers = nn.ModuleList()
+    for _ in range(2 * num_stages):                       # even = self, odd = cross (attention_gnn.py:84-88)
+        layer, module, mha = _Holder(), _Holder(), _Holder()
+        for name in ('in_proj_q', 'in_proj_k', 'in_proj_v', 'out_proj'):
+            setattr(mha, name, nn.Conv1d(d, d, kernel_size=1))
+        module.mha = mha
+        module.fc = _feed_forward_params(2 * d, 2 * d, d)
+        layer.module = module
+        gnn.layers.append(layer)
+    return gnn
+
+
+class SuperGlue(nn.Module):
+    """B200-native matching core behind the reference's module API.
+
+    Extra (optional) config keys, ignored by the reference: ``precision`` ('fp32' | 'tf32x3'),
+    ``match_threshold`` (used by :class:`MatchingCore`).
+    """
+
+    def __init__(self, config: dict):
+        super().__init__()
+        self.config: dict = config
+        d = config['descriptor_dim']
+        pe, gnn = config['positional_encoding'], config['attention_gnn']
+        if pe.get('encoder_name', 'FeedForwardNet') != 'FeedForwardNet':
+            # same error type the reference raises for an unknown encoder (models/superglue/__init__.py:40-42)
+            raise NameError(f"{pe['encoder_name']} positional encoder is not provided by openglue_b200 "
+                            "(only 'FeedForwardNet')")
+        if gnn.get('attention', 'softmax') != 'softmax':
+            raise ValueError(f"Attention type {gnn['attention']} is not supported (only 'softmax').")
+        if gnn.get('embed_dim', d) != d or pe.get('output_size', d) != d:
+            raise ValueError('embed_dim / positional_encoding.output_size must equal descriptor_dim')
+        if config.get('no_descriptors', False):
+            raise ValueError('no_descriptors=True is not supported by openglue_b200')
+        hidden = list(pe.get('hidden_layers_sizes') or [])
+        self.positional_encoding = _Holder()
+        self.positional_encoding.encoder = _feed_forward_params(pe.get('side_info_size', 1) + 2, *hidden, d)
+        self.attention_gnn = _gnn_params(gnn['num_stages'], d)
+        self.residual = config.get('residual', False)
+        if self.residual:
+            self.mix_coefs = nn.parameter.Parameter(torch.zeros(d, 1))
+        self.linear_proj = nn.Conv1d(d, d, kernel_size=1)
+        self.dustbin_score = nn.Parameter(torch.tensor(float(config['dustbin_score_init'])))
+
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._ogcfg: Optional[_cabi.OgConfig] = None
+        self.last_launches = 0
+
+        weights_path = config.get('weights', None)
+        if weights_path is not None:
+            print('SuperGlue loading... ', self.load_state_dict(torch.load(str(weights_path), map_location='cpu')))
+
+    # ------------------------------------------------------------------ weights
+    def _precision(self) -> int:
+        return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3}[self.config.get('precision', 'fp32')]
+
+    def og_config(self) -> _cabi.OgConfig:
+        return _cabi.make_config(self.config, self.config.get('match_threshold', 0.2), self._precision())
+
+    def invalidate_packed(self) -> None:
+        self._packed = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode: bool = True):
+        if mode:
+            self._packed = None
+        return super().train(mode)
+
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed_weights(self, device: torch.device) -> torch.Tensor:
+        """Folded + packed weights on ``device`` (cached; rebuilt when a parameter changes)."""
+        key = (self._weights_version(), str(device), self._precision())
+        if self._packed is None or self._packed_key != key:
+            self._ogcfg = self.og_config()
+            self._packed = pack_weights(self.state_dict(), self.config, self._ogcfg).to(device)
+            self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _image_wh(data: dict, idx: int):
+        """reference superglue.py:35-38: image tensor [..., H, W] or image{idx}_size = (W, H)."""
+        if 'image0' in data and 'image1' in data:
+            sz = data[f'image{idx}'].size()
+            return float(sz[-1]), float(sz[-2])
+        w, h = data[f'image{idx}_size'][:2]
+        return float(w), float(h)
+
+    def run(self, data: dict, want_matches: bool, want_context: bool = True) -> Dict[str, torch.Tensor]:
+        if self.training:
+            raise RuntimeError('openglue_b200.SuperGlue implements the eval-mode forward pass only '
+                               '(train-mode BatchNorm statistics and backward are not built yet)')
+        k0, k1 = data['keypoints0'], data['keypoints1']
+        dev = k0.device
+        if dev.type != 'cuda':
+            raise RuntimeError('openglue_b200.SuperGlue needs CUDA tensors (sm_100a); there is no CPU path')
+
+        def prep(t, last):
+            t = t.detach()
+            if t.dtype != torch.float32:
+                t = t.float()
+            if t.shape[-1] != last:
+                raise ValueError(f'expected last dimension {last}, got {tuple(t.shape)}')
+            return t.contiguous()
+
+        d = self.config['descriptor_dim']
+        s_dim = self.config['positional_encoding'].get('side_info_size', 1)
+        k0, k1 = prep(k0, 2), prep(k1, 2)
+        d0, d1 = prep(data['local_descriptors0'], d), prep(data['local_descriptors1'], d)
+        s0, s1 = prep(data['side_info0'], s_dim), prep(data['side_info1'], s_dim)
+        B, n, m = k0.shape[0], k0.shape[1], k1.shape[1]
+        if k1.shape[0] != B or d0.shape[:2] != (B, n) or d1.shape[:2] != (B, m) or s0.shape[:2] != (B, n) \
+                or s1.shape[:2] != (B, m):
+            raise ValueError('inconsistent batch / keypoint counts in data')
+        if n == 0 or m == 0:
+            raise ValueError('empty keypoint set')
+        w0, h0 = self._image_wh(data, 0)
+        w1, h1 = self._image_wh(data, 1)
+
+        lib = _cabi.lib()
+        with torch.cuda.device(dev):
+            packed = self.packed_weights(dev)
+            cfg = self._ogcfg
+            ws_bytes = lib.og_workspace_bytes(cfg, B, n, m)
+            if ws_bytes < 0:
+                _cabi.check(int(ws_bytes), 'og_workspace_bytes')
+            if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
+                self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            scores = torch.empty(B, n + 1, m + 1, dtype=torch.float32, device=dev)
+            out = {'scores': scores}
+            ctx0 = ctx1 = None
+            if want_context:
+                ctx0 = torch.empty(B, d, n, dtype=torch.float32, device=dev)
+                ctx1 = torch.empty(B, d, m, dtype=torch.float32, device=dev)
+                out['context_descriptors0'], out['context_descriptors1'] = ctx0, ctx1
+            m0 = ms0 = m1 = ms1 = None
+            if want_matches:
+                m0 = torch.empty(B, n, dtype=torch.int64, device=dev)
+                ms0 = torch.empty(B, n, dtype=torch.float32, device=dev)
+                m1 = torch.empty(B, m, dtype=torch.int64, device=dev)
+                ms1 = torch.empty(B, m, dtype=torch.float32, device=dev)
+                out.update(matches0=m0, matching_scores0=ms0, matches1=m1, matching_scores1=ms1)
+            wh = (C.c_float * 4)(w0, h0, w1, h1)
+            ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+            rc = lib.og_superglue_forward(cfg, ptr(packed), B, n, m, ptr(k0), ptr(k1), ptr(s0), ptr(s1), ptr(d0),
+                                          ptr(d1), wh, ptr(ctx0), ptr(ctx1), ptr(scores), ptr(m0), ptr(ms0),
+                                          ptr(m1), ptr(ms1), ptr(self._workspace), ws_bytes,
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _cabi.check(rc, 'og_superglue_forward')
+            self.last_launches = lib.og_last_forward_launches()
+        return out
+
+    def forward(self, data: dict) -> Dict[str, torch.Tensor]:
+        """-> {'context_descriptors0' [B,d,N], 'context_descriptors1' [B,d,M], 'scores' [B,N+1,M+1]}"""
+        return self.run(data, want_matches=False)
+
+
+class MatchingCore(nn.Module):
+    """``SuperGlue`` + mutual-argmax match extraction: what ``MatchingTrainingModule.forward``
+    (reference models/matching_module.py:149-187) computes from prepared features, fused into the
+    same C-ABI call.  Accepts host (CPU) tensors too: they are copied to ``device`` (pinned ->
+    non-blocking) and ``matches0`` / ``matching_scores0`` come back on the host."""
+
+    def __init__(self, superglue: SuperGlue, match_threshold: float = 0.2, device: Optional[torch.device] = None):
+        super().__init__()
+        self.superglue = superglue
+        self.superglue.config['match_threshold'] = match_threshold
+        self.superglue.invalidate_packed()
+        self.device = torch.device(device) if device is not None else None
+
+    _TENSOR_KEYS = ('keypoints0', 'keypoints1', 'side_info0', 'side_info1', 'local_descriptors0', 'local_descriptors1')
+
+    def forward(self, data: dict, want_scores: bool = False) -> Dict[str, torch.Tensor]:
+        host = data['keypoints0'].device.type == 'cpu'
+        if host:
+            dev = self.device or torch.device('cuda', torch.cuda.current_device())
+            data = dict(data)
+            for k in self._TENSOR_KEYS:
+                data[k] = data[k].to(dev, non_blocking=True)
+        out = self.superglue.run(data, want_matches=True, want_context=False)
+        res = {'matches0': out['matches0'], 'matching_scores0': out['matching_scores0'],
+               'matches1': out['matches1'], 'matching_scores1': out['matching_scores1']}
+        if want_scores:
+            res['scores'] = out['scores']
+        if host:
+            res = {k: v.to('cpu', non_blocking=True) for k, v in res.items()}
+            torch.cuda.current_stream().synchronize()
+        return res

@@ -1,0 +1,101 @@
+"""CPU-only checks of the host side: state_dict contract, config translation, the C-ABI
+library (loads, exports every declared symbol, argument validation without touching a GPU),
+weight folding/packing, and that the product never routes through the oracle."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN_FULL
+from openglue_b200 import _cabi
+from openglue_b200.packing import pack_weights
+from openglue_b200.superglue import SuperGlue
+from openglue_b200.synthetic import default_config, synthetic_state_dict
+from oracle import superglue_oracle as O
+from packed_emulation import forward_packed
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, 'include', 'openglue_b200.h')).read()
+    declared = set(re.findall(r'\b(og_[a-z0-9_]+)\s*\(', header))
+    declared -= {'og_status', 'og_config'}
+    lib = _cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    assert lib.og_version() == 100
+
+
+def test_abi_struct_sizes_match_header():
+    # og_config: 5 + 8 ints, int, float, float, int = 17 * 4 bytes
+    import ctypes as C
+    assert C.sizeof(_cabi.OgConfig) == 17 * 4
+    assert C.sizeof(_cabi.OgLinearArgs) == 192
+
+
+def test_argument_validation_without_gpu():
+    lib = _cabi.lib()
+    cfg = _cabi.make_config(default_config())
+    assert lib.og_workspace_bytes(cfg, 0, 10, 10) < 0
+    assert b'positive' in lib.og_last_error()
+    bad = _cabi.make_config(default_config(descriptor_dim=30, num_heads=4))
+    assert lib.og_packed_weight_floats(bad) < 0
+    assert lib.og_superglue_forward(cfg, None, 1, 8, 8, None, None, None, None, None, None, None, None, None, None,
+                                    None, None, None, None, None, 0, None) == -1     # OG_EINVAL, no CUDA call made
+    assert lib.og_workspace_bytes(cfg, 2, 100, 3000) < 0                             # > 2048 columns: unsupported
+
+
+def test_state_dict_contract_matches_reference_layout(golden):
+    for name in ['tiny_flat', 'tiny_offset_s6']:
+        fx = golden(name)
+        model = SuperGlue(dict(fx['config']))
+        ours = model.state_dict()
+        assert list(ours.keys()) == list(fx['state_dict'].keys())
+        for k, v in fx['state_dict'].items():
+            assert tuple(ours[k].shape) == tuple(v.shape), k
+        model.load_state_dict(fx['state_dict'], strict=True)
+    full = SuperGlue(default_config())
+    assert len(full.state_dict()) == 333
+    assert sum(p.numel() for p in full.parameters()) == 11_957_249
+
+
+def test_unsupported_options_raise():
+    cfg = default_config()
+    cfg['attention_gnn']['attention'] = 'linear'
+    with pytest.raises(ValueError):
+        SuperGlue(cfg)
+    cfg = default_config()
+    cfg['positional_encoding']['encoder_name'] = 'Nope'
+    with pytest.raises(NameError):
+        SuperGlue(cfg)
+    model = SuperGlue(default_config(descriptor_dim=32, num_stages=1)).eval()
+    data = {'keypoints0': torch.zeros(1, 4, 2), 'keypoints1': torch.zeros(1, 4, 2)}
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        model(data)
+
+
+@pytest.mark.parametrize('name', GOLDEN_FULL)
+def test_weight_folding_and_packing(golden, name):
+    """packed weights + the kernel schedule (torch emulation, fp64) == oracle fp64."""
+    fx = golden(name)
+    cfg = _cabi.make_config(fx['config'])
+    packed64 = pack_weights(fx['state_dict'], fx['config'], cfg, dtype=torch.float64)
+    got = forward_packed(packed64, fx['config'], cfg, fx['data'])
+    assert (got['scores'] - fx['scores_f64']).abs().max() < 5e-6     # the reference keeps log_a/log_b/norm in fp32
+    ref = O.run(fx['state_dict'], fx['config'], fx['data'], dtype=torch.float64)
+    assert (got['context_descriptors0'] - ref['context_descriptors0']).abs().max() < 1e-10
+    # and the fp32 packing is the rounding of the fp64 one
+    packed = pack_weights(fx['state_dict'], fx['config'], cfg)
+    assert packed.dtype == torch.float32
+    assert (packed.double() - packed64).abs().max() <= packed64.abs().max() * 2 ** -23
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'openglue_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), f
+                assert '/root/reference' not in text, f
