@@ -85,6 +85,9 @@ typedef enum og_tensor_id {
 } og_tensor_id;
 
 int64_t og_packed_weight_floats(const og_config* cfg);
+/* hi = round-to-nearest tf32(src), lo = round-to-nearest tf32(src - hi): the operand split of the
+ * OG_PREC_TF32X3 kernels (x ~= hi + lo to 2^-23 |x|).  Device pointers, n floats each.            */
+int og_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream);
 int64_t og_packed_offset(const og_config* cfg, int tensor_id, int index);
 
 /* ---------------------------------------------------------------------------------------------
@@ -97,11 +100,14 @@ int64_t og_packed_offset(const og_config* cfg, int tensor_id, int index);
  *   ctx{0,1}   [B, d, n|m]  channel-first context descriptors   (may be NULL)
  *   scores     [B, n+1, m+1] log assignment incl. dustbins
  *   matches0   [B, n] int64 (-1 = no match), mscores0 [B, n];  matches1/mscores1 [B, m] (may be NULL)
+ *   packed_hi/lo  tf32 split of packed_weights (og_split_tf32), same offsets; required when
+ *              cfg->precision == OG_PREC_TF32X3, ignored (may be NULL) for OG_PREC_FP32
  *   workspace  >= og_workspace_bytes(cfg, B, n, m), 256-byte aligned
  * ------------------------------------------------------------------------------------------- */
 int64_t og_workspace_bytes(const og_config* cfg, int batch, int n, int m);
 
 int og_superglue_forward(const og_config* cfg, const float* packed_weights,
+                         const float* packed_hi, const float* packed_lo,
                          int batch, int n, int m,
                          const float* kpts0, const float* kpts1,
                          const float* side0, const float* side1,
@@ -142,6 +148,12 @@ typedef struct og_linear_args {
   float* Yt; int64_t ldyt; int64_t strideYt;
 } og_linear_args;
 int og_linear_fwd(const og_linear_args* args, int precision, void* stream);
+/* Tensor-core (tcgen05, 3xTF32) form of og_linear_fwd: W is given pre-split (Whi/Wlo, same layout as
+ * args->W, which is ignored).  mode 0: A operand through TMEM (production), 1: A through shared
+ * memory (cross-check).  Yhi/Ylo (Ythi/Ytlo): optional split copies of Y (Yt) for use as the next
+ * kernel's B operand; same ld/stride as Y (Yt).                                                    */
+int og_linear_tc_fwd(const og_linear_args* args, const float* Whi, const float* Wlo,
+                     float* Yhi, float* Ylo, float* Ythi, float* Ytlo, int mode, void* stream);
 
 /* out[b, i, h*Dh + c] = sum_j softmax_j(q_i . k_j * Dh^-0.5) v_j[c]  per head h.
  * Replaces softmax_attention (models/superglue/attention.py:8-19) inside

@@ -51,7 +51,9 @@ SYMBOLS = {
     'og_packed_weight_floats': (_L, [_CFG]),
     'og_packed_offset': (_L, [_CFG, _I, _I]),
     'og_workspace_bytes': (_L, [_CFG, _I, _I, _I]),
-    'og_superglue_forward': (_I, [_CFG, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float),
+    'og_split_tf32': (_I, [_P, _P, _P, _L, _P]),
+    'og_linear_tc_fwd': (_I, [C.POINTER(OgLinearArgs), _P, _P, _P, _P, _P, _P, _I, _P]),
+    'og_superglue_forward': (_I, [_CFG, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     'og_last_forward_launches': (_I, []),
     'og_linear_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P]),

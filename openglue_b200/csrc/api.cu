@@ -2,6 +2,7 @@
 // host-side schedule of the whole matching-core forward pass.
 #include "common.cuh"
 #include "linear_simt.cuh"
+#include "linear_tc.cuh"
 #include "attention_simt.cuh"
 #include "sinkhorn.cuh"
 #include "match.cuh"
@@ -65,7 +66,7 @@ static Layout make_layout(const og_config* c) {
 }
 
 struct Workspace {
-  float *in0, *h0, *h1, *x, *qkv, *o, *hid, *g, *sbuf;
+  float *in0, *h0, *h1, *x, *qkv, *o, *hid, *g, *ghi, *glo, *sbuf;
   void *sink, *match;
   int64_t lds, sink_bytes, match_bytes, total;
 };
@@ -85,6 +86,8 @@ static int plan_workspace(const og_config* c, int B, int n, int m, void* base, W
   w->o = (float*)take(R * d * 4);
   w->hid = (float*)take(R * 2 * d * 4);
   w->g = (float*)take(R * d * 4);
+  w->ghi = (float*)take((int64_t)B * m * d * 4);          // tf32 split of image-1 descriptors (score GEMM B operand)
+  w->glo = (float*)take((int64_t)B * m * d * 4);
   w->lds = align_up(m, 4);
   w->sbuf = (float*)take((int64_t)B * n * w->lds * 4);
   w->sink_bytes = sinkhorn_workspace_bytes(B, n, m);
@@ -105,9 +108,42 @@ static og_linear_args lin(const float* A, int64_t lda, int k, const float* W, co
   return a;
 }
 
-static int linear_dispatch(const og_linear_args& a, int precision, cudaStream_t s) {
-  // OG_PREC_TF32X3 (tcgen05) is routed here once its kernels land; fp32 is the exact path.
-  (void)precision;
+static TcLinearArgs to_tc_args(const og_linear_args& a) {
+  TcLinearArgs t;
+  memset(&t, 0, sizeof(t));
+  t.A = a.A; t.lda = a.lda; t.strideA = a.strideA; t.A2 = a.A2; t.lda2 = a.lda2; t.strideA2 = a.strideA2;
+  t.k1 = a.k1; t.k2 = a.k2;
+  t.b_rows_per_batch = a.strideW ? (int)(a.strideW / a.ldw) : 0;
+  t.bias = a.bias; t.rows = a.rows; t.nout = a.nout; t.batch = a.batch; t.alpha = a.alpha; t.relu = a.relu;
+  t.R = a.R; t.ldr = a.ldr; t.strideR = a.strideR; t.rscale = a.rscale;
+  t.Y = a.Y; t.ldy = a.ldy; t.strideY = a.strideY; t.Yt = a.Yt; t.ldyt = a.ldyt; t.strideYt = a.strideYt;
+  return t;
+}
+
+// Split-output request for the tensor-core path (the fp32 CUDA-core path ignores it).
+struct SplitOut { float *Yhi = nullptr, *Ylo = nullptr, *Ythi = nullptr, *Ytlo = nullptr; };
+
+static int linear_tc_run(const og_linear_args& a, const float* Whi, const float* Wlo, const SplitOut& so, int mode,
+                         cudaStream_t s) {
+  TcLinearArgs t = to_tc_args(a);
+  t.Yhi = so.Yhi; t.Ylo = so.Ylo; t.Ythi = so.Ythi; t.Ytlo = so.Ytlo;
+  if (a.strideW && a.strideW % a.ldw != 0) return fail(OG_EUNSUPPORTED, "linear_tc: strideW must be a multiple of ldw");
+  if (!linear_tc_eligible(t, Whi, Wlo, a.ldw))
+    return fail(OG_EUNSUPPORTED, "linear_tc: needs K >= 32, K %% 4 == 0 and 16-byte aligned rows");
+  const int64_t brows = a.strideW ? (int64_t)t.b_rows_per_batch * a.batch : a.nout;
+  return mode == tcl::MODE_SS ? linear_tc_launch_mode<tcl::MODE_SS>(t, Whi, Wlo, a.ldw, brows, s)
+                              : linear_tc_launch_mode<tcl::MODE_TS>(t, Whi, Wlo, a.ldw, brows, s);
+}
+
+// Kernel selection for one linear layer: tcgen05 3xTF32 when asked for and the shape is tileable,
+// otherwise the fp32 CUDA-core kernel (tiny K such as the 3-channel keypoint-encoder input).
+static int linear_dispatch(const og_linear_args& a, int precision, cudaStream_t s, const float* Whi = nullptr,
+                           const float* Wlo = nullptr, const SplitOut& so = SplitOut()) {
+  if (precision == OG_PREC_TF32X3 && Whi && Wlo) {
+    TcLinearArgs t = to_tc_args(a);
+    if (linear_tc_eligible(t, Whi, Wlo, a.ldw)) return linear_tc_run(a, Whi, Wlo, so, tcl::MODE_TS, s);
+  }
+  if (so.Yhi || so.Ythi) return fail(OG_EUNSUPPORTED, "split outputs need the tensor-core path");
   return linear_simt_launch(a, s);
 }
 
@@ -174,9 +210,26 @@ int og_last_forward_launches(void) { return launch_counter(); }
 
 int og_linear_fwd(const og_linear_args* a, int precision, void* stream) {
   OG_CHECK_ARG(a && a->A && a->W && (a->Y || a->Yt), "linear: null pointer");
+  OG_CHECK_ARG(precision == OG_PREC_FP32, "linear: the tensor-core form takes pre-split weights (og_linear_tc_fwd)");
   OG_CHECK_ARG(a->rows > 0 && a->nout > 0 && a->batch > 0 && a->k1 > 0 && a->k2 >= 0, "linear: bad sizes");
   OG_CHECK_ARG(a->k2 == 0 || a->A2, "linear: k2 > 0 needs A2");
   return linear_dispatch(*a, precision, (cudaStream_t)stream);
+}
+
+int og_linear_tc_fwd(const og_linear_args* a, const float* Whi, const float* Wlo, float* Yhi, float* Ylo, float* Ythi,
+                     float* Ytlo, int mode, void* stream) {
+  OG_CHECK_ARG(a && a->A && Whi && Wlo && (a->Y || a->Yt || Yhi || Ythi), "linear_tc: null pointer");
+  OG_CHECK_ARG(a->rows > 0 && a->nout > 0 && a->batch > 0 && a->k1 > 0 && a->k2 >= 0, "linear_tc: bad sizes");
+  OG_CHECK_ARG((Yhi == nullptr) == (Ylo == nullptr) && (Ythi == nullptr) == (Ytlo == nullptr), "linear_tc: hi/lo come in pairs");
+  SplitOut so; so.Yhi = Yhi; so.Ylo = Ylo; so.Ythi = Ythi; so.Ytlo = Ytlo;
+  return linear_tc_run(*a, Whi, Wlo, so, mode, (cudaStream_t)stream);
+}
+
+int og_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream) {
+  OG_CHECK_ARG(src && hi && lo && n > 0, "split_tf32: bad arguments");
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n);
+  OG_LAUNCH_CHECK("split_tf32_kernel");
+  return OG_OK;
 }
 
 int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq, const float* k, int64_t ldk, int64_t stridek,
@@ -209,7 +262,8 @@ int og_match_fwd(const float* scores, int batch, int n, int m, float threshold, 
                       workspace_bytes, (cudaStream_t)stream);
 }
 
-int og_superglue_forward(const og_config* cfg, const float* Wp, int B, int n, int m, const float* kpts0,
+int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, int B, int n, int m,
+                         const float* kpts0,
                          const float* kpts1, const float* side0, const float* side1, const float* desc0,
                          const float* desc1, const float* img_wh, float* ctx0, float* ctx1, float* scores,
                          int64_t* matches0, float* mscores0, int64_t* matches1, float* mscores1, void* workspace,
@@ -219,6 +273,10 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, int B, int n, in
   OG_CHECK_ARG(Wp && kpts0 && kpts1 && desc0 && desc1 && img_wh && scores && workspace, "forward: null pointer");
   OG_CHECK_ARG(cfg->side_info_size == 0 || (side0 && side1), "forward: side info missing");
   OG_CHECK_ARG(B > 0 && n > 0 && m > 0, "forward: batch, n, m must be positive");
+  OG_CHECK_ARG(cfg->precision == OG_PREC_FP32 || (Whi && Wlo), "forward: OG_PREC_TF32X3 needs packed_hi / packed_lo");
+  const bool tcp = (cfg->precision == OG_PREC_TF32X3) && cfg->descriptor_dim >= 32;   // K >= 32 for the tcgen05 tiles
+  auto WH = [&](int64_t off) { return tcp ? Whi + off : nullptr; };
+  auto WL = [&](int64_t off) { return tcp ? Wlo + off : nullptr; };
   OG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream_;
   const int prec = cfg->precision;
@@ -276,17 +334,17 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, int B, int n, in
     float* xr = w.x + (int64_t)row0 * d;
     og_linear_args a = lin(xr, d, d, Wp + L.fc1_w[l], Wp + L.fc1_b[l], rows, 2 * d, w.hid + (int64_t)row0 * 2 * d, 2 * d);
     a.A2 = w.o + (int64_t)row0 * d; a.lda2 = d; a.k2 = d; a.ldw = 2 * d; a.relu = 1;
-    int r = linear_dispatch(a, prec, st);
+    int r = linear_dispatch(a, prec, st, WH(L.fc1_w[l]), WL(L.fc1_w[l]));
     if (r != OG_OK) return r;
     og_linear_args c2 = lin(w.hid + (int64_t)row0 * 2 * d, 2 * d, 2 * d, Wp + L.fc2_w[l], Wp + L.fc2_b[l], rows, d, xr, d);
     c2.R = xr; c2.ldr = d;
-    return linear_dispatch(c2, prec, st);
+    return linear_dispatch(c2, prec, st, WH(L.fc2_w[l]), WL(L.fc2_w[l]));
   };
   auto project = [&](int l, int row0, int rows, int wrow0, int nout) -> int {
     // qkv[rows, wrow0 : wrow0 + nout] = x[rows] . Wqkv[wrow0 : wrow0 + nout]^T + b
     og_linear_args a = lin(w.x + (int64_t)row0 * d, d, d, Wp + L.qkv_w[l] + (int64_t)wrow0 * d, Wp + L.qkv_b[l] + wrow0,
                            rows, nout, w.qkv + (int64_t)row0 * 3 * d + wrow0, 3 * d);
-    return linear_dispatch(a, prec, st);
+    return linear_dispatch(a, prec, st, WH(L.qkv_w[l] + (int64_t)wrow0 * d), WL(L.qkv_w[l] + (int64_t)wrow0 * d));
   };
   for (int l = 0; l < cfg->num_layers; ++l) {
     if (l % 2 == 0) {                                      // self: both images, shared weights, independent
@@ -320,14 +378,16 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, int B, int n, in
     a.R = img ? desc1 : desc0; a.ldr = d; a.strideR = (int64_t)nn * d; a.rscale = Wp + L.proj_rmix;
     float* ctx = img ? ctx1 : ctx0;
     if (ctx) { a.Yt = ctx; a.ldyt = nn; a.strideYt = (int64_t)d * nn; }
-    if ((rc = linear_dispatch(a, prec, st)) != OG_OK) return rc;
+    SplitOut so;
+    if (tcp && img == 1) { so.Yhi = w.ghi; so.Ylo = w.glo; }      // image-1 descriptors are the score GEMM's B operand
+    if ((rc = linear_dispatch(a, prec, st, WH(L.proj_w), WL(L.proj_w), so)) != OG_OK) return rc;
   }
   // ---- score matrix (superglue.py:64,80-86): S = g0^T g1 * d^-0.5, written with padded rows ----
   {
     og_linear_args a = lin(w.g, d, d, w.g + (int64_t)R0 * d, nullptr, n, m, w.sbuf, w.lds);
     a.batch = B; a.strideA = (int64_t)n * d; a.strideW = (int64_t)m * d; a.strideY = (int64_t)n * w.lds;
     a.alpha = (float)pow((double)d, -0.5);
-    if ((rc = linear_dispatch(a, prec, st)) != OG_OK) return rc;
+    if ((rc = linear_dispatch(a, prec, st, tcp ? w.ghi : nullptr, tcp ? w.glo : nullptr)) != OG_OK) return rc;
   }
   // ---- optimal transport (superglue.py:88-111) + matches (matching_module.py:174-187) ----
   rc = sinkhorn_launch(w.sbuf, w.lds, (int64_t)n * w.lds, Wp + L.dustbin, B, n, m, cfg->sinkhorn_iters,

@@ -236,8 +236,9 @@ inline int64_t sinkhorn_workspace_bytes(int B, int n, int m) {
 template <int V>
 inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream) {
   static bool attr_set = false;
-  if (!attr_set) {
-    OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  if (!attr_set) {                       // largest request of this instantiation: m = 128 V  =>  mpad = 128 V + 4
+    OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((1 + SINK_WARPS) * (128 * V + 4) * sizeof(float))));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};

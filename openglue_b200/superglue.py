@@ -85,6 +85,8 @@ class SuperGlue(nn.Module):
 
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._packed_hi: Optional[torch.Tensor] = None
+        self._packed_lo: Optional[torch.Tensor] = None
         self._workspace: Optional[torch.Tensor] = None
         self._ogcfg: Optional[_cabi.OgConfig] = None
         self.last_launches = 0
@@ -121,6 +123,14 @@ class SuperGlue(nn.Module):
         if self._packed is None or self._packed_key != key:
             self._ogcfg = self.og_config()
             self._packed = pack_weights(self.state_dict(), self.config, self._ogcfg).to(device)
+            self._packed_hi = self._packed_lo = None
+            if self._precision() == _cabi.OG_PREC_TF32X3:      # operand split for the tcgen05 kernels
+                self._packed_hi, self._packed_lo = torch.empty_like(self._packed), torch.empty_like(self._packed)
+                with torch.cuda.device(device):
+                    _cabi.check(_cabi.lib().og_split_tf32(
+                        C.c_void_p(self._packed.data_ptr()), C.c_void_p(self._packed_hi.data_ptr()),
+                        C.c_void_p(self._packed_lo.data_ptr()), self._packed.numel(),
+                        C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), 'og_split_tf32')
             self._packed_key = key
         return self._packed
 
@@ -190,7 +200,7 @@ class SuperGlue(nn.Module):
                 out.update(matches0=m0, matching_scores0=ms0, matches1=m1, matching_scores1=ms1)
             wh = (C.c_float * 4)(w0, h0, w1, h1)
             ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-            rc = lib.og_superglue_forward(cfg, ptr(packed), B, n, m, ptr(k0), ptr(k1), ptr(s0), ptr(s1), ptr(d0),
+            rc = lib.og_superglue_forward(cfg, ptr(packed), ptr(self._packed_hi), ptr(self._packed_lo), B, n, m, ptr(k0), ptr(k1), ptr(s0), ptr(s1), ptr(d0),
                                           ptr(d1), wh, ptr(ctx0), ptr(ctx1), ptr(scores), ptr(m0), ptr(ms0),
                                           ptr(m1), ptr(ms1), ptr(self._workspace), ws_bytes,
                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))

@@ -1,0 +1,80 @@
+"""GPU tests of the tcgen05 (3xTF32) kernels: operator-level vs fp64, and the whole path in
+precision='tf32x3' against the reference golden vectors (same 1e-4 bound as the fp32 mode)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from conftest import GOLDEN_FULL
+from openglue_b200 import _cabi
+from openglue_b200.superglue import MatchingCore, SuperGlue
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('rows,k1,k2,nout,batch,per_batch_b', [(128, 32, 0, 128, 1, False), (1000, 256, 256, 392, 1, False),
+                                                              (257, 64, 0, 200, 3, True), (300, 512, 0, 256, 2, False)])
+def test_linear_tc_operator(mode, rows, k1, k2, nout, batch, per_batch_b):
+    g = torch.Generator().manual_seed(0)
+    K = k1 + k2
+    A = 3 * torch.randn(batch, rows, k1, generator=g)
+    A2 = torch.randn(batch, rows, k2, generator=g) if k2 else None
+    W = torch.randn(batch if per_batch_b else 1, nout, K, generator=g)
+    bias = torch.randn(nout, generator=g)
+    R = torch.randn(batch, rows, nout, generator=g)
+    X = torch.cat([A, A2], -1) if k2 else A
+    ref = (0.5 * (X.double() @ W.double().transpose(1, 2)) + bias.double()).relu() + R.double()
+    lib = _cabi.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dA, dW, db, dR = A.to(DEV), W.to(DEV), bias.to(DEV), R.to(DEV)
+    dA2 = A2.to(DEV) if k2 else None
+    Whi, Wlo = torch.empty_like(dW), torch.empty_like(dW)
+    _cabi.check(lib.og_split_tf32(_p(dW), _p(Whi), _p(Wlo), dW.numel(), st), 'og_split_tf32')
+    Y = torch.full((batch, rows, nout), float('nan'), device=DEV)
+    Yhi, Ylo = torch.zeros_like(Y), torch.zeros_like(Y)
+    Yt = torch.full((batch, nout, rows), float('nan'), device=DEV)
+    Ythi, Ytlo = torch.zeros_like(Yt), torch.zeros_like(Yt)
+    a = _cabi.OgLinearArgs()
+    a.A, a.lda, a.strideA = dA.data_ptr(), k1, rows * k1
+    if k2:
+        a.A2, a.lda2, a.strideA2 = dA2.data_ptr(), k2, rows * k2
+    a.k1, a.k2, a.ldw, a.strideW = k1, k2, K, (nout * K if per_batch_b else 0)
+    a.bias = db.data_ptr()
+    a.rows, a.nout, a.batch, a.alpha, a.relu = rows, nout, batch, 0.5, 1
+    a.R, a.ldr, a.strideR = dR.data_ptr(), nout, rows * nout
+    a.Y, a.ldy, a.strideY = Y.data_ptr(), nout, rows * nout
+    a.Yt, a.ldyt, a.strideYt = Yt.data_ptr(), rows, nout * rows
+    _cabi.check(lib.og_linear_tc_fwd(C.byref(a), _p(Whi), _p(Wlo), _p(Yhi), _p(Ylo), _p(Ythi), _p(Ytlo), mode, st),
+                'og_linear_tc_fwd')
+    scale = ref.abs().max()
+    assert (Y.cpu().double() - ref).abs().max() <= 4e-6 * scale        # fp32-grade (single-pass tf32 would be ~1e-3)
+    assert torch.equal(Yt.transpose(1, 2), Y)
+    assert (Yhi.double() + Ylo.double() - Y.double()).abs().max() <= 2.0 ** -21 * scale
+    assert torch.equal(Ythi.transpose(1, 2), Yhi) and torch.equal(Ytlo.transpose(1, 2), Ylo)
+
+
+@pytest.mark.parametrize('name', ['tiny_planted', 'small_planted', 'C1_planted', 'C1_flat'])
+def test_forward_tf32x3_matches_reference(golden, name):
+    fx = golden(name)
+    cfg = dict(fx['config'])
+    cfg['precision'] = 'tf32x3'
+    model = SuperGlue(cfg).eval()
+    model.load_state_dict(fx['state_dict'])
+    model = model.to(DEV)
+    data = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in fx['data'].items()}
+    res = MatchingCore(model, fx['match_threshold'])(data, want_scores=True)
+    bound = max(1e-4, 2 * fx['ref32_vs_ref64_max_abs'])
+    s = res['scores'].cpu()
+    if 'scores_f64' in fx:
+        assert (s.double() - fx['scores_f64']).abs().max() <= bound
+    else:
+        assert (s[:, ::7, ::5].double() - fx['scores_f64_sample']).abs().max() <= bound
+    if 'planted' in name:
+        assert torch.equal(res['matches0'].cpu(), fx['matches0'])
+        assert (res['matching_scores0'].cpu() - fx['matching_scores0']).abs().max() <= 1e-4

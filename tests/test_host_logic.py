@@ -41,7 +41,7 @@ def test_argument_validation_without_gpu():
     assert b'positive' in lib.og_last_error()
     bad = _cabi.make_config(default_config(descriptor_dim=30, num_heads=4))
     assert lib.og_packed_weight_floats(bad) < 0
-    assert lib.og_superglue_forward(cfg, None, 1, 8, 8, None, None, None, None, None, None, None, None, None, None,
+    assert lib.og_superglue_forward(cfg, None, None, None, 1, 8, 8, None, None, None, None, None, None, None, None, None, None,
                                     None, None, None, None, None, 0, None) == -1     # OG_EINVAL, no CUDA call made
     assert lib.og_workspace_bytes(cfg, 2, 100, 3000) < 0                             # > 2048 columns: unsupported
 
