@@ -167,6 +167,16 @@ int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq,
                      int batch, int nq, int nk, int num_heads, int head_dim,
                      int precision, void* stream);
 
+/* Tensor-core (tcgen05, 3xTF32) form of og_attention_fwd.  Operands as the projection GEMM leaves them:
+ *   q fp32 [batch][nq, ldq];  khi/klo tf32-split [batch*nk, ldk] keypoint-major;
+ *   vthi/vtlo tf32-split [batch*d, ldvt] channel-major (d = num_heads*head_dim; ldvt >= nk, multiple of 4).
+ * head_dim must be 32 or 64.                                                                        */
+int og_attention_tc_fwd(const float* q, int64_t ldq, int64_t strideq,
+                        const float* khi, const float* klo, int64_t ldk,
+                        const float* vthi, const float* vtlo, int64_t ldvt,
+                        float* out, int64_t ldo, int64_t strideo,
+                        int batch, int nq, int nk, int num_heads, int head_dim, void* stream);
+
 /* Dustbin-augmented log-domain Sinkhorn.  Replaces SuperGlue.get_matching_probs
  * (superglue.py:88-111) + log_otp_solver (optimal_transport.py:4-28).
  *   S       [B][n, lds]  inner score block (lds >= m, multiple of 4, 16-byte aligned rows)

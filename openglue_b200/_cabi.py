@@ -58,6 +58,7 @@ SYMBOLS = {
     'og_last_forward_launches': (_I, []),
     'og_linear_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P]),
     'og_attention_fwd': (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
+    'og_attention_tc_fwd': (_I, [_P, _L, _L, _P, _P, _L, _P, _P, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P]),
     'og_sinkhorn_workspace_bytes': (_L, [_I, _I, _I]),
     'og_sinkhorn_fwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _L, _P]),
     'og_match_workspace_bytes': (_L, [_I, _I, _I]),

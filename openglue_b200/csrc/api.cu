@@ -4,6 +4,7 @@
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
 #include "attention_simt.cuh"
+#include "attention_tc.cuh"
 #include "sinkhorn.cuh"
 #include "match.cuh"
 #include <math.h>
@@ -67,6 +68,8 @@ static Layout make_layout(const og_config* c) {
 
 struct Workspace {
   float *in0, *h0, *h1, *x, *qkv, *o, *hid, *g, *ghi, *glo, *sbuf;
+  float *q, *khi, *klo, *vthi, *vtlo;     // tensor-core attention operands (OG_PREC_TF32X3)
+  int64_t ldn, ldm;                       // padded row lengths of the channel-major V^T buffers
   void *sink, *match;
   int64_t lds, sink_bytes, match_bytes, total;
 };
@@ -88,6 +91,16 @@ static int plan_workspace(const og_config* c, int B, int n, int m, void* base, W
   w->g = (float*)take(R * d * 4);
   w->ghi = (float*)take((int64_t)B * m * d * 4);          // tf32 split of image-1 descriptors (score GEMM B operand)
   w->glo = (float*)take((int64_t)B * m * d * 4);
+  w->ldn = align_up(n, 4); w->ldm = align_up(m, 4);
+  if (c->precision == OG_PREC_TF32X3) {
+    w->q = (float*)take(R * d * 4);
+    w->khi = (float*)take(R * d * 4);
+    w->klo = (float*)take(R * d * 4);
+    w->vthi = (float*)take((int64_t)B * d * (w->ldn + w->ldm) * 4);
+    w->vtlo = (float*)take((int64_t)B * d * (w->ldn + w->ldm) * 4);
+  } else {
+    w->q = w->khi = w->klo = w->vthi = w->vtlo = nullptr;
+  }
   w->lds = align_up(m, 4);
   w->sbuf = (float*)take((int64_t)B * n * w->lds * 4);
   w->sink_bytes = sinkhorn_workspace_bytes(B, n, m);
@@ -242,6 +255,18 @@ int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq, const float* 
   return attention_dispatch(a, head_dim, precision, (cudaStream_t)stream);
 }
 
+int og_attention_tc_fwd(const float* q, int64_t ldq, int64_t strideq, const float* khi, const float* klo, int64_t ldk,
+                        const float* vthi, const float* vtlo, int64_t ldvt, float* out, int64_t ldo, int64_t strideo,
+                        int batch, int nq, int nk, int num_heads, int head_dim, void* stream) {
+  OG_CHECK_ARG(q && khi && klo && vthi && vtlo && out, "attention_tc: null pointer");
+  OG_CHECK_ARG(batch > 0 && nq > 0 && nk > 0 && num_heads > 0, "attention_tc: bad sizes");
+  if (!attention_tc_eligible(head_dim, ldq, ldk, ldvt, ldo))
+    return fail(OG_EUNSUPPORTED, "attention_tc: head_dim in {32, 64} and 16-byte aligned rows required");
+  TcAttnArgs a{q, ldq, strideq, out, ldo, strideo, batch, nq, nk, num_heads, num_heads * head_dim,
+               (float)pow((double)head_dim, -0.5)};
+  return attention_tc_launch(a, khi, klo, ldk, vthi, vtlo, ldvt, head_dim, (cudaStream_t)stream);
+}
+
 int64_t og_sinkhorn_workspace_bytes(int batch, int n, int m) { return sinkhorn_workspace_bytes(batch, n, m); }
 
 int og_sinkhorn_fwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin, int batch, int n, int m,
@@ -346,7 +371,59 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi
                            rows, nout, w.qkv + (int64_t)row0 * 3 * d + wrow0, 3 * d);
     return linear_dispatch(a, prec, st, WH(L.qkv_w[l] + (int64_t)wrow0 * d), WL(L.qkv_w[l] + (int64_t)wrow0 * d));
   };
+  // Tensor-core attention path (OG_PREC_TF32X3, Dh in {32, 64}): the projection GEMM writes Q as fp32, K split
+  // hi/lo keypoint-major and V split hi/lo channel-major (= the reference's own [B, d, M] layout), which are
+  // exactly the operand layouts csrc/attention_tc.cuh stages with TMA.
+  const bool tca_ok = tcp && (dh == 32 || dh == 64);
+  auto project_tc = [&](int l, int qrow0, int nq_rows, int srow0, int ns, int sbatch) -> int {
+    // q rows [qrow0, +nq_rows);  k / v from source rows [srow0, +sbatch*ns) (sbatch sequences of ns keypoints)
+    int r;
+    og_linear_args aq = lin(w.x + (int64_t)qrow0 * d, d, d, Wp + L.qkv_w[l], Wp + L.qkv_b[l], nq_rows, d,
+                            w.q + (int64_t)qrow0 * d, d);
+    if ((r = linear_dispatch(aq, prec, st, WH(L.qkv_w[l]), WL(L.qkv_w[l]))) != OG_OK) return r;
+    og_linear_args ak = lin(w.x + (int64_t)srow0 * d, d, d, Wp + L.qkv_w[l] + (int64_t)d * d, Wp + L.qkv_b[l] + d,
+                            sbatch * ns, d, nullptr, d);
+    SplitOut sk; sk.Yhi = w.khi + (int64_t)srow0 * d; sk.Ylo = w.klo + (int64_t)srow0 * d;
+    if ((r = linear_dispatch(ak, prec, st, WH(L.qkv_w[l] + (int64_t)d * d), WL(L.qkv_w[l] + (int64_t)d * d), sk)) != OG_OK) return r;
+    const int64_t ldv = (srow0 == 0) ? w.ldn : w.ldm;
+    const int64_t voff = (srow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
+    og_linear_args av = lin(w.x + (int64_t)srow0 * d, d, d, Wp + L.qkv_w[l] + 2 * (int64_t)d * d, Wp + L.qkv_b[l] + 2 * d,
+                            ns, d, nullptr, d);
+    av.batch = sbatch; av.strideA = (int64_t)ns * d; av.ldyt = ldv; av.strideYt = (int64_t)d * ldv;
+    SplitOut sv; sv.Ythi = w.vthi + voff; sv.Ytlo = w.vtlo + voff;
+    return linear_dispatch(av, prec, st, WH(L.qkv_w[l] + 2 * (int64_t)d * d), WL(L.qkv_w[l] + 2 * (int64_t)d * d), sv);
+  };
+  auto attend_tc = [&](int qrow0, int nq, int krow0, int nk, int batch) -> int {
+    const int64_t ldv = (krow0 == 0) ? w.ldn : w.ldm;
+    const int64_t voff = (krow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
+    TcAttnArgs a{w.q + (int64_t)qrow0 * d, d, (int64_t)nq * d, w.o + (int64_t)qrow0 * d, d, (int64_t)nq * d,
+                 batch, nq, nk, H, d, (float)pow((double)dh, -0.5)};
+    return attention_tc_launch(a, w.khi + (int64_t)krow0 * d, w.klo + (int64_t)krow0 * d, d, w.vthi + voff, w.vtlo + voff,
+                               ldv, dh, st);
+  };
   for (int l = 0; l < cfg->num_layers; ++l) {
+    if (tca_ok) {
+      if (l % 2 == 0) {                                    // self
+        if (n == m) {
+          if ((rc = project_tc(l, 0, R, 0, n, 2 * B)) != OG_OK) return rc;
+          if ((rc = attend_tc(0, n, 0, n, 2 * B)) != OG_OK) return rc;
+        } else {
+          if ((rc = project_tc(l, 0, R0, 0, n, B)) != OG_OK) return rc;
+          if ((rc = attend_tc(0, n, 0, n, B)) != OG_OK) return rc;
+          if ((rc = project_tc(l, R0, R1, R0, m, B)) != OG_OK) return rc;
+          if ((rc = attend_tc(R0, m, R0, m, B)) != OG_OK) return rc;
+        }
+        if ((rc = mlp(l, 0, R)) != OG_OK) return rc;
+      } else {                                             // cross: SEQUENTIAL (attention_gnn.py:74-77)
+        if ((rc = project_tc(l, 0, R0, R0, m, B)) != OG_OK) return rc;
+        if ((rc = attend_tc(0, n, R0, m, B)) != OG_OK) return rc;
+        if ((rc = mlp(l, 0, R0)) != OG_OK) return rc;
+        if ((rc = project_tc(l, R0, R1, 0, n, B)) != OG_OK) return rc;     // k, v of the UPDATED image 0
+        if ((rc = attend_tc(R0, m, 0, n, B)) != OG_OK) return rc;
+        if ((rc = mlp(l, R0, R1)) != OG_OK) return rc;
+      }
+      continue;
+    }
     if (l % 2 == 0) {                                      // self: both images, shared weights, independent
       if ((rc = project(l, 0, R, 0, 3 * d)) != OG_OK) return rc;
       if (n == m) {

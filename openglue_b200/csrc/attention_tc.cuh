@@ -1,0 +1,317 @@
+// tcgen05 fused multi-head softmax attention with fp32-grade accuracy ("3xTF32").
+// Replaces softmax_attention (reference models/superglue/attention.py:8-19); the N x M probability
+// tensor never exists outside TMEM.
+//
+// One CTA = 128 queries of one (batch, head); key blocks of 64.
+//   S_i  = Q . K_i^T      A = Q hi/lo resident in TMEM (split once), B = K_i hi/lo tiles (TMA, smem)
+//   P_i  = exp(S_i*scale - m_i)   by 128 softmax threads, one query row each (row max / sum are
+//                                 thread-local: no shuffles), written back to TMEM split hi/lo
+//   O_i  = P_i . V_i      A = P_i hi/lo in TMEM, B = V_i^T hi/lo tiles (TMA, smem), fresh accumulator
+//   acc  = acc * exp(m_{i-1} - m_i) + O_i      in registers of the softmax threads
+// Every contraction is three tf32 MMAs (lo.hi + hi.lo + hi.hi) with fp32 accumulation in TMEM.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = softmax /
+// correction / epilogue.  S/P and O are double buffered in TMEM so the tensor pipe works on block
+// i+1 while the softmax threads handle block i.
+//
+// Operand layouts in HBM (written by the projection GEMM's epilogue, csrc/linear_tc.cuh):
+//   Q        fp32  [rows, ldq]            keypoint-major, head h = columns [h*Dh, (h+1)*Dh)
+//   K hi/lo  tf32  [batch*nk, ldk]        keypoint-major
+//   Vt hi/lo tf32  [batch*d, ldvt]        channel-major (the reference's own [B, d, M] layout)
+#pragma once
+#include "tc_common.cuh"
+#include <math_constants.h>
+
+namespace og {
+
+struct TcAttnArgs {
+  const float* q; int64_t ldq, strideq;        // strideq: floats between batch items
+  float* out; int64_t ldo, strideo;
+  int batch, nq, nk, num_heads, d;
+  float scale;
+};
+
+namespace tca {
+constexpr int BM = 128, BNK = 64;               // queries per CTA, keys per block
+constexpr int STAGES = 3;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+// TMEM columns:  Q_hi [0,64)  Q_lo [64,128)  SP_j [128+128j, +128) = {S / P_hi: 64, P_lo: 64}  O_j [384+64j, +64)
+constexpr int COL_QHI = 0, COL_QLO = 64, COL_SP = 128, COL_O = 384;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct __align__(8) Barriers {
+  uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
+  uint64_t q_ready, s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint32_t tmem_base;
+};
+template <int DH> __host__ __device__ constexpr int k_stage_bytes() { return 2 * BNK * DH * 4; }        // hi + lo
+template <int DH> __host__ __device__ constexpr int v_stage_bytes() { return 2 * DH * BNK * 4; }
+template <int DH> __host__ __device__ constexpr int smem_bytes() { return 1024 + STAGES * (k_stage_bytes<DH>() + v_stage_bytes<DH>()) + 512; }
+}  // namespace tca
+
+template <int DH>
+__global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_khi,
+                                                                       const __grid_constant__ CUtensorMap map_klo,
+                                                                       const __grid_constant__ CUtensorMap map_vhi,
+                                                                       const __grid_constant__ CUtensorMap map_vlo,
+                                                                       TcAttnArgs a) {
+  using namespace tca;
+  using namespace tc;
+  static_assert(DH == 32 || DH == 64, "head_dim 32 or 64");
+  constexpr int KBLK = BNK * 128;                 // bytes of one [64 keys x 32 ch] K block
+  constexpr int VBLK = DH * 128;                  // bytes of one [DH ch x 32 keys] V^T block
+  constexpr int K_HALF = (DH / 32) * KBLK;        // hi (or lo) part of a K stage
+  constexpr int V_HALF = 2 * VBLK;
+
+  extern __shared__ uint8_t og_tca_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tca_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + STAGES * k_stage_bytes<DH>();
+  Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<DH>());
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (a.nk + BNK - 1) / BNK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&bars->k_full[i], 1); mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
+    }
+    mbar_init(&bars->q_ready, 128);
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 128);
+      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 128);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
+    prefetch_tensormap(&map_vhi); prefetch_tensormap(&map_vlo);
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int krow0 = b * a.nk;                   // K rows of this batch item
+      const int vrow = b * a.d + h * DH;            // V^T rows (channels) of this (batch, head)
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(&bars->k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[s], k_stage_bytes<DH>());
+        uint8_t* kd = sK + s * k_stage_bytes<DH>();
+#pragma unroll
+        for (int cb = 0; cb < DH / 32; ++cb) {
+          tma_load_2d(kd + cb * KBLK, &map_khi, &bars->k_full[s], h * DH + cb * 32, krow0 + i * BNK);
+          tma_load_2d(kd + K_HALF + cb * KBLK, &map_klo, &bars->k_full[s], h * DH + cb * 32, krow0 + i * BNK);
+        }
+        mbar_wait(&bars->v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[s], v_stage_bytes<DH>());
+        uint8_t* vd = sV + s * v_stage_bytes<DH>();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(vd + kb * VBLK, &map_vhi, &bars->v_full[s], i * BNK + kb * 32, vrow);
+          tma_load_2d(vd + V_HALF + kb * VBLK, &map_vlo, &bars->v_full[s], i * BNK + kb * 32, vrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_qk = make_idesc_tf32(BM, BNK);
+    const uint32_t idesc_pv = make_idesc_tf32(BM, DH);
+    auto issue_qk = [&](int i) {
+      const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
+      mbar_wait(&bars->k_full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH>()), klo = khi + K_HALF;
+        const uint32_t d_s = tmem + COL_SP + 128 * j;
+#pragma unroll
+        for (int kk = 0; kk < DH / 8; ++kk) {
+          const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
+          const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
+          umma_tf32_ts(d_s, tmem + COL_QLO + kk * 8, dhi, idesc_qk, kk ? 1u : 0u);
+          umma_tf32_ts(d_s, tmem + COL_QHI + kk * 8, dlo, idesc_qk, 1u);
+          umma_tf32_ts(d_s, tmem + COL_QHI + kk * 8, dhi, idesc_qk, 1u);
+        }
+        umma_commit(&bars->k_empty[s]);
+        umma_commit(&bars->s_full[j]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&bars->q_ready, 0);
+    tc_fence_after();
+    issue_qk(0);
+    for (int i = 0; i < nblk; ++i) {
+      if (i + 1 < nblk) issue_qk(i + 1);            // keep the tensor pipe fed while block i is in softmax
+      const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1, jph = (i >> 1) & 1;
+      mbar_wait(&bars->v_full[s], ph);
+      mbar_wait(&bars->p_full[j], jph);
+      mbar_wait(&bars->o_empty[j], jph ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH>()), vlo = vhi + V_HALF;
+        const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
+        const uint32_t d_o = tmem + COL_O + 64 * j;
+#pragma unroll
+        for (int kk = 0; kk < BNK / 8; ++kk) {
+          const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
+          const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
+          umma_tf32_ts(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
+          umma_tf32_ts(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
+          umma_tf32_ts(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
+        }
+        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->o_full[j]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int qd = warp & 3;
+    const int trow = qd * 32 + lane;
+    const int grow = q0 + trow;
+    const bool row_ok = grow < a.nq;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+
+    {   // Q row -> split -> TMEM (A operand of every QK^T)
+      const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH;
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        tmem_st_32x32(tmem + lane_base + COL_QHI + c0, hi);
+        tmem_st_32x32(tmem + lane_base + COL_QLO + c0, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->q_ready);
+    }
+
+    float acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f, prev_corr = 0.f;
+    const float sc = a.scale;
+
+    auto fold_o = [&](int i, float corr) {        // acc = acc * corr + O_i
+      const int j = i & 1, jph = (i >> 1) & 1;
+      mbar_wait(&bars->o_full[j], jph);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(tmem + lane_base + COL_O + 64 * j + c0, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(acc[c0 + c], corr, __uint_as_float(o[c]));
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->o_empty[j]);
+    };
+
+    for (int i = 0; i < nblk; ++i) {
+      const int j = i & 1, jph = (i >> 1) & 1;
+      const uint32_t sp = tmem + lane_base + COL_SP + 128 * j;
+      const int kbase = i * BNK;
+      mbar_wait(&bars->s_full[j], jph);
+      tc_fence_after();
+      // pass A: block max of the scaled logits (keys beyond nk masked)
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c0 = 0; c0 < BNK; c0 += 32) {
+        uint32_t s[32];
+        tmem_ld_32x32(sp + c0, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v = (kbase + c0 + c < a.nk) ? __uint_as_float(s[c]) * sc : -CUDART_INF_F;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = ex2_approx((m_run - m_new) * LOG2E);        // exp2(-inf) = 0 on the first block
+      // pass B: p = exp(s - m_new), split, back to TMEM (P_hi over S, P_lo beside it)
+      float rs = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < BNK; c0 += 32) {
+        uint32_t s[32], lo[32];
+        tmem_ld_32x32(sp + c0, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v = (kbase + c0 + c < a.nk) ? __uint_as_float(s[c]) * sc : -CUDART_INF_F;
+          const float p = ex2_approx((v - m_new) * LOG2E);
+          rs += p;
+          split_tf32(p, s[c], lo[c]);
+        }
+        tmem_st_32x32(sp + c0, s);
+        tmem_st_32x32(sp + 64 + c0, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[j]);
+      l_run = fmaf(l_run, corr, rs);
+      m_run = m_new;
+      if (i >= 1) fold_o(i - 1, prev_corr);
+      prev_corr = corr;
+    }
+    fold_o(nblk - 1, prev_corr);
+
+    if (row_ok) {
+      const float inv = 1.f / l_run;
+      float* orow = a.out + (int64_t)b * a.strideo + (int64_t)grow * a.ldo + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH; c += 4)
+        *reinterpret_cast<float4*>(orow + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<tca::TMEM_COLS>(tmem); }
+}
+
+// khi/klo: [batch*nk, ldk];  vthi/vtlo: [batch*d, ldvt]
+inline int attention_tc_launch(const TcAttnArgs& a, const float* khi, const float* klo, int64_t ldk, const float* vthi,
+                               const float* vtlo, int64_t ldvt, int head_dim, cudaStream_t stream) {
+  using namespace tca;
+  CUtensorMap mkh, mkl, mvh, mvl;
+  int rc;
+  if ((rc = tc::make_tmap_2d(&mkh, khi, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mkl, klo, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mvh, vthi, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, head_dim)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, head_dim)) != OG_OK) return rc;
+  dim3 grid(cdiv(a.nq, BM), a.num_heads, a.batch);
+#define OG_TCA_CASE(DH_)                                                                                      \
+  case DH_: {                                                                                                 \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      OG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<DH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                   smem_bytes<DH_>()));                                                       \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    attention_tc_kernel<DH_><<<grid, THREADS, smem_bytes<DH_>(), stream>>>(mkh, mkl, mvh, mvl, a);            \
+  } break;
+  switch (head_dim) {
+    OG_TCA_CASE(32) OG_TCA_CASE(64)
+    default: return fail(OG_EUNSUPPORTED, "attention_tc: head_dim %d not in {32, 64}", head_dim);
+  }
+#undef OG_TCA_CASE
+  OG_LAUNCH_CHECK("attention_tc_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+inline bool attention_tc_eligible(int head_dim, int64_t ldq, int64_t ldk, int64_t ldvt, int64_t ldo) {
+  return (head_dim == 32 || head_dim == 64) && ldq % 4 == 0 && ldk % 4 == 0 && ldvt % 4 == 0 && ldo % 4 == 0;
+}
+
+}  // namespace og

@@ -47,9 +47,16 @@ def _stream():
 def decisive_rows(scores_ref, margin):
     """rows/cols of the inner block whose top-2 gap exceeds `margin` (argmax is then well defined)."""
     inner = scores_ref[:, :-1, :-1].double()
-    t2r = inner.topk(2, dim=2).values
-    t2c = inner.topk(2, dim=1).values
-    return (t2r[..., 0] - t2r[..., 1]) > margin, (t2c[:, 0] - t2c[:, 1]) > margin
+    b, n, m = inner.shape
+    row_ok = torch.ones(b, n, dtype=torch.bool)
+    col_ok = torch.ones(b, m, dtype=torch.bool)
+    if m >= 2:
+        t2r = inner.topk(2, dim=2).values
+        row_ok = (t2r[..., 0] - t2r[..., 1]) > margin
+    if n >= 2:
+        t2c = inner.topk(2, dim=1).values
+        col_ok = (t2c[:, 0] - t2c[:, 1]) > margin
+    return row_ok, col_ok
 
 
 def check_matches(ours, ref, scores_ref, tol):
