@@ -283,9 +283,22 @@ def main():
     p = lambda t, off=0: C.c_void_p(t.data_ptr() + off * 4)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    def attn():
-        _cabi.check(lib.og_attention_fwd(p(qkv), 3 * d, n * 3 * d, p(qkv, d), 3 * d, n * 3 * d, p(qkv, 2 * d), 3 * d,
-                                         n * 3 * d, p(o), d, n * d, nb, n, n, H, d // H, prec, st), 'og_attention_fwd')
+    if args.precision == 'tf32x3':
+        kk = torch.randn(nb * n, d, device=dev)
+        ldv = (n + 3) // 4 * 4
+        vt = torch.randn(nb * d, ldv, device=dev)
+        khi, klo, vthi, vtlo = (torch.empty_like(t) for t in (kk, kk, vt, vt))
+        _cabi.check(lib.og_split_tf32(p(kk), p(khi), p(klo), kk.numel(), st), 'og_split_tf32')
+        _cabi.check(lib.og_split_tf32(p(vt), p(vthi), p(vtlo), vt.numel(), st), 'og_split_tf32')
+        qq = torch.randn(nb * n, d, device=dev)
+
+        def attn():
+            _cabi.check(lib.og_attention_tc_fwd(p(qq), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), ldv, p(o), d, n * d,
+                                                nb, n, n, H, d // H, st), 'og_attention_tc_fwd')
+    else:
+        def attn():
+            _cabi.check(lib.og_attention_fwd(p(qkv), 3 * d, n * 3 * d, p(qkv, d), 3 * d, n * 3 * d, p(qkv, 2 * d), 3 * d,
+                                             n * 3 * d, p(o), d, n * d, nb, n, n, H, d // H, prec, st), 'og_attention_fwd')
     for _ in range(3):
         attn()
     reps = 10

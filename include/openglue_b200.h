@@ -149,8 +149,9 @@ typedef struct og_linear_args {
 } og_linear_args;
 int og_linear_fwd(const og_linear_args* args, int precision, void* stream);
 /* Tensor-core (tcgen05, 3xTF32) form of og_linear_fwd: W is given pre-split (Whi/Wlo, same layout as
- * args->W, which is ignored).  mode 0: A operand through TMEM (production), 1: A through shared
- * memory (cross-check).  Yhi/Ylo (Ythi/Ytlo): optional split copies of Y (Yt) for use as the next
+ * args->W, which is ignored).  mode 2: production kernel (persistent, TMA-fed, chunked accumulation
+ * drained with round-to-nearest adds); mode 0 / 1: first-generation kernel with the A operand through
+ * TMEM / through shared memory (kept as cross-checks of the descriptor and TMEM-operand paths).  Yhi/Ylo (Ythi/Ytlo): optional split copies of Y (Yt) for use as the next
  * kernel's B operand; same ld/stride as Y (Yt).                                                    */
 int og_linear_tc_fwd(const og_linear_args* args, const float* Whi, const float* Wlo,
                      float* Yhi, float* Ylo, float* Ythi, float* Ytlo, int mode, void* stream);

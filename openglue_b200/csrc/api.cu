@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "linear_simt.cuh"
 #include "linear_tc.cuh"
+#include "linear_tc2.cuh"
 #include "attention_simt.cuh"
 #include "attention_tc.cuh"
 #include "sinkhorn.cuh"
@@ -144,6 +145,10 @@ static int linear_tc_run(const og_linear_args& a, const float* Whi, const float*
   if (!linear_tc_eligible(t, Whi, Wlo, a.ldw))
     return fail(OG_EUNSUPPORTED, "linear_tc: needs K >= 32, K %% 4 == 0 and 16-byte aligned rows");
   const int64_t brows = a.strideW ? (int64_t)t.b_rows_per_batch * a.batch : a.nout;
+  if (mode == 2) {                       // production kernel: persistent, chunked accumulation
+    if (!linear_tc2_eligible(t, Whi, Wlo, a.ldw)) return fail(OG_EUNSUPPORTED, "linear_tc2: needs dense batches and k1 %% 32 == 0 for concat");
+    return linear_tc2_launch(t, Whi, Wlo, a.ldw, brows, s);
+  }
   return mode == tcl::MODE_SS ? linear_tc_launch_mode<tcl::MODE_SS>(t, Whi, Wlo, a.ldw, brows, s)
                               : linear_tc_launch_mode<tcl::MODE_TS>(t, Whi, Wlo, a.ldw, brows, s);
 }
@@ -154,6 +159,7 @@ static int linear_dispatch(const og_linear_args& a, int precision, cudaStream_t 
                            const float* Wlo = nullptr, const SplitOut& so = SplitOut()) {
   if (precision == OG_PREC_TF32X3 && Whi && Wlo) {
     TcLinearArgs t = to_tc_args(a);
+    if (linear_tc2_eligible(t, Whi, Wlo, a.ldw)) return linear_tc_run(a, Whi, Wlo, so, 2, s);
     if (linear_tc_eligible(t, Whi, Wlo, a.ldw)) return linear_tc_run(a, Whi, Wlo, so, tcl::MODE_TS, s);
   }
   if (so.Yhi || so.Ythi) return fail(OG_EUNSUPPORTED, "split outputs need the tensor-core path");

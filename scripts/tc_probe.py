@@ -79,6 +79,14 @@ CASES = [
     ('ts_resid_split_t', (0, 300, 512, 0, 256, 2, 0, 0, 1, 1, 1, 0)),
     ('ts_batchedB',     (0, 257, 64, 0, 200, 3, 1, 0, 0, 0, 0, 0)),
     ('ss_tails_concat', (1, 1000, 256, 256, 392, 1, 0, 1, 0, 0, 0, 0)),
+    ('v2_k256',         (2, 128, 256, 0, 128, 1, 0, 0, 0, 0, 0, 0)),
+    ('v2_tails_concat', (2, 1000, 256, 256, 392, 1, 0, 1, 0, 0, 0, 0)),
+    ('v2_resid_split_t', (2, 300, 512, 0, 256, 2, 0, 0, 1, 1, 1, 0)),
+    ('v2_batchedB',     (2, 257, 64, 0, 200, 3, 1, 0, 0, 0, 0, 0)),
+    ('v2_qkv_shape_time', (2, 65536, 256, 0, 768, 1, 0, 0, 0, 0, 0, 10)),
+    ('v2_fc1_shape_time', (2, 65536, 256, 256, 512, 1, 0, 1, 0, 0, 0, 10)),
+    ('v2_fc2_shape_time', (2, 65536, 512, 0, 256, 1, 0, 0, 1, 0, 0, 10)),
+    ('v2_score_shape_time', (2, 2048, 256, 0, 2048, 16, 1, 0, 0, 0, 0, 10)),
     ('ts_qkv_shape_time', (0, 65536, 256, 0, 768, 1, 0, 0, 0, 0, 0, 10)),
     ('ts_fc1_shape_time', (0, 65536, 256, 256, 512, 1, 0, 1, 0, 0, 0, 10)),
     ('ss_qkv_shape_time', (1, 65536, 256, 0, 768, 1, 0, 0, 0, 0, 0, 10)),

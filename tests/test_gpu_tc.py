@@ -17,7 +17,7 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [2, 0, 1])
 @pytest.mark.parametrize('rows,k1,k2,nout,batch,per_batch_b', [(128, 32, 0, 128, 1, False), (1000, 256, 256, 392, 1, False),
                                                               (257, 64, 0, 200, 3, True), (300, 512, 0, 256, 2, False)])
 def test_linear_tc_operator(mode, rows, k1, k2, nout, batch, per_batch_b):
@@ -53,7 +53,9 @@ def test_linear_tc_operator(mode, rows, k1, k2, nout, batch, per_batch_b):
     _cabi.check(lib.og_linear_tc_fwd(C.byref(a), _p(Whi), _p(Wlo), _p(Yhi), _p(Ylo), _p(Ythi), _p(Ytlo), mode, st),
                 'og_linear_tc_fwd')
     scale = ref.abs().max()
-    assert (Y.cpu().double() - ref).abs().max() <= 1e-5 * scale        # fp32-grade (single-pass tf32 would be ~1e-3)
+    # mode 2 (chunked accumulation) is as accurate as an fp32 FMA GEMM; modes 0/1 carry the tensor core's
+    # truncating accumulator over the whole K (still ~100x better than single-pass tf32)
+    assert (Y.cpu().double() - ref).abs().max() <= (1.5e-6 if mode == 2 else 1e-5) * scale
     assert torch.equal(Yt.transpose(1, 2), Y)
     assert (Yhi.double() + Ylo.double() - Y.double()).abs().max() <= 2.0 ** -21 * scale
     assert torch.equal(Ythi.transpose(1, 2), Yhi) and torch.equal(Ytlo.transpose(1, 2), Ylo)
