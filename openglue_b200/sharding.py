@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing for the matching core: image pairs are independent, so a batch is cut into
+contiguous shards, one per rank (one process per GPU), with NO collective on the data path.  The
+only exchange is the reduction of per-rank match statistics - what the reference's
+``self.log(..., sync_dist=True)`` does (models/matching_module.py:102-103, 127-128)."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+
+def shard_range(total_pairs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous split: rank r gets pairs [start, start+count); the first (total % world) ranks get one extra."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f'rank {rank} outside world of {world_size}')
+    base, extra = divmod(total_pairs, world_size)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def shard_pairs(data: Dict[str, object], rank: int, world_size: int) -> Dict[str, object]:
+    """Slice every batched tensor of a ``data`` dict (superglue.py:30-38 keys) to this rank's pairs."""
+    total = data['keypoints0'].shape[0]
+    start, count = shard_range(total, rank, world_size)
+    return {k: (v[start:start + count] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == total else v)
+            for k, v in data.items()}
+
+
+def match_statistics(matches0: torch.Tensor, matching_scores0: torch.Tensor) -> torch.Tensor:
+    """[#pairs, #matches, sum of match confidences] of a shard (float64, on the tensors' device)."""
+    ok = matches0 >= 0
+    return torch.stack([torch.tensor(float(matches0.shape[0]), device=matches0.device, dtype=torch.float64),
+                        ok.sum().double(), matching_scores0.double()[ok].sum()])
+
+
+def all_reduce_statistics(stats: torch.Tensor, group=None) -> Dict[str, float]:
+    """Sum the per-rank statistics over the process group (NCCL on GPUs, gloo on CPU) and derive the means."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    pairs, nmatch, conf = (float(x) for x in stats.tolist())
+    return {'pairs': pairs, 'matches_per_pair': nmatch / max(pairs, 1.0), 'mean_confidence': conf / max(nmatch, 1.0)}

@@ -1,0 +1,68 @@
+"""Run the three dominant kernels once each at the headline (C3) shapes - the target of
+`ncu --set full -k regex:...` captures.   python scripts/prof_ops.py [attn|linear|sinkhorn|all] [reps]"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from openglue_b200 import _cabi
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+dev = 'cuda:0'
+lib = _cabi.lib()
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+B, n, d, H = 16, 2048, 256, 4
+torch.manual_seed(0)
+
+
+def split(t):
+    hi, lo = torch.empty_like(t), torch.empty_like(t)
+    _cabi.check(lib.og_split_tf32(p(t), p(hi), p(lo), t.numel(), st), 'split')
+    return hi, lo
+
+
+if which in ('attn', 'all'):
+    nb = 2 * B
+    q = torch.randn(nb * n, d, device=dev)
+    k = torch.randn(nb * n, d, device=dev)
+    vt = torch.randn(nb * d, n, device=dev)
+    khi, klo = split(k)
+    vthi, vtlo = split(vt)
+    o = torch.empty(nb * n, d, device=dev)
+    for _ in range(reps):
+        _cabi.check(lib.og_attention_tc_fwd(p(q), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), n, p(o), d, n * d,
+                                            nb, n, n, H, d // H, st), 'attn')
+if which in ('linear', 'all'):
+    rows = 2 * B * n
+    for (k1, k2, nout, relu, resid) in ((256, 0, 256, 0, 0), (256, 256, 512, 1, 0), (512, 0, 256, 0, 1)):
+        A = torch.randn(rows, k1, device=dev)
+        A2 = torch.randn(rows, k2, device=dev) if k2 else None
+        W = torch.randn(nout, k1 + k2, device=dev)
+        Whi, Wlo = split(W)
+        bias = torch.randn(nout, device=dev)
+        Y = torch.randn(rows, nout, device=dev)
+        a = _cabi.OgLinearArgs()
+        a.A, a.lda, a.strideA = A.data_ptr(), k1, 0
+        if k2:
+            a.A2, a.lda2, a.strideA2 = A2.data_ptr(), k2, 0
+        a.k1, a.k2, a.ldw, a.strideW = k1, k2, k1 + k2, 0
+        a.bias = bias.data_ptr()
+        a.rows, a.nout, a.batch, a.alpha, a.relu = rows, nout, 1, 1.0, relu
+        if resid:
+            a.R, a.ldr, a.strideR = Y.data_ptr(), nout, 0
+        a.Y, a.ldy, a.strideY = Y.data_ptr(), nout, 0
+        for _ in range(reps):
+            _cabi.check(lib.og_linear_tc_fwd(C.byref(a), p(Whi), p(Wlo), None, None, None, None, 2, st), 'linear')
+if which in ('sinkhorn', 'all'):
+    S = torch.randn(B, n, n, device=dev) * 4
+    scores = torch.empty(B, n + 1, n + 1, device=dev)
+    dust = torch.ones(1, device=dev)
+    wsb = lib.og_sinkhorn_workspace_bytes(B, n, n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    for _ in range(reps):
+        _cabi.check(lib.og_sinkhorn_fwd(p(S), n, n * n, p(dust), B, n, n, 100, 1.0, p(scores), p(ws), wsb, st), 'sinkhorn')
+torch.cuda.synchronize()
+print('done')
