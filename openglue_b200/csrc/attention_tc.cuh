@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
-          split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
         tmem_st_32x32(tmem + lane_base + COL_QHI + c0, hi);
         tmem_st_32x32(tmem + lane_base + COL_QLO + c0, lo);
@@ -199,8 +199,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     float acc[DH];
 #pragma unroll
     for (int c = 0; c < DH; ++c) acc[c] = 0.f;
-    float m_run = -CUDART_INF_F, l_run = 0.f, prev_corr = 0.f;
-    const float sc = a.scale;
+    // Online softmax in the exp2 domain.  c1 = scale*log2(e); mc = fl(m*c1) is the running max in that domain and
+    // is used consistently for p = 2^(s*c1 - mc) (one FFMA: the product is exact inside the fma, only the small
+    // difference is rounded) and for the block-to-block correction 2^(mc_old - mc_new).
+    const float c1 = a.scale * LOG2E;
+    float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, prev_corr = 0.f, next_corr = 0.f;
 
     auto fold_o = [&](int i, float corr) {        // acc = acc * corr + O_i
       const int j = i & 1, jph = (i >> 1) & 1;
@@ -218,41 +221,55 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_arrive(&bars->o_empty[j]);
     };
 
-    for (int i = 0; i < nblk; ++i) {
+    // iteration i: softmax of block i (i < nblk), then fold of O_{i-1} (i >= 1); one inlined copy of each
+#pragma unroll 1
+    for (int i = 0; i <= nblk; ++i) {
+      if (i < nblk) {
       const int j = i & 1, jph = (i >> 1) & 1;
       const uint32_t sp = tmem + lane_base + COL_SP + 128 * j;
       const int kbase = i * BNK;
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
-      // pass A: block max of the scaled logits (keys beyond nk masked)
+      const bool tail = kbase + BNK > a.nk;                          // last block only: mask keys >= nk
+      // pass A: block max.  The chunk loops are deliberately NOT unrolled: the per-block code must stay
+      // resident in the instruction cache (the fully unrolled first version spent 25% of its issue slots in no_inst).
       float mx = -CUDART_INF_F;
-#pragma unroll
+#pragma unroll 1
       for (int c0 = 0; c0 < BNK; c0 += 32) {
         uint32_t s[32];
         tmem_ld_32x32(sp + c0, s);
         tmem_wait_ld();
+        if (tail) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float v = (kbase + c0 + c < a.nk) ? __uint_as_float(s[c]) * sc : -CUDART_INF_F;
-          mx = fmaxf(mx, v);
+          for (int c = 0; c < 32; ++c) if (kbase + c0 + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
         }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = ex2_approx((m_run - m_new) * LOG2E);        // exp2(-inf) = 0 on the first block
-      // pass B: p = exp(s - m_new), split, back to TMEM (P_hi over S, P_lo beside it)
-      float rs = 0.f;
 #pragma unroll
+        for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
+      }
+      const float m_new = fmaxf(m_run, mx);                          // raw logits (scale > 0 commutes with max)
+      const float mc = m_new * c1;
+      const float corr = ex2_approx(mc_run - mc);                    // 2^(-inf) = 0 on the first block
+      // pass B: p = 2^(s*c1 - mc), split, back to TMEM (P_hi over S, P_lo beside it)
+      float rs = 0.f;
+#pragma unroll 1
       for (int c0 = 0; c0 < BNK; c0 += 32) {
         uint32_t s[32], lo[32];
         tmem_ld_32x32(sp + c0, s);
         tmem_wait_ld();
+        if (tail) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float v = (kbase + c0 + c < a.nk) ? __uint_as_float(s[c]) * sc : -CUDART_INF_F;
-          const float p = ex2_approx((v - m_new) * LOG2E);
-          rs += p;
-          split_tf32(p, s[c], lo[c]);
+          for (int c = 0; c < 32; ++c) if (kbase + c0 + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
         }
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), c1, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), c1, -mc));
+          r0 += p0; r1 += p1;
+          split_tf32_fast(p0, s[c], lo[c]);
+          split_tf32_fast(p1, s[c + 1], lo[c + 1]);
+        }
+        rs += r0 + r1;
         tmem_st_32x32(sp + c0, s);
         tmem_st_32x32(sp + 64 + c0, lo);
       }
@@ -260,11 +277,12 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       tc_fence_before();
       mbar_arrive(&bars->p_full[j]);
       l_run = fmaf(l_run, corr, rs);
-      m_run = m_new;
+      m_run = m_new; mc_run = mc;
+      next_corr = corr;
+      }
       if (i >= 1) fold_o(i - 1, prev_corr);
-      prev_corr = corr;
+      prev_corr = next_corr;
     }
-    fold_o(nblk - 1, prev_corr);
 
     if (row_ok) {
       const float inv = 1.f / l_run;

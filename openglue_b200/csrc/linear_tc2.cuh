@@ -37,7 +37,7 @@ constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512;
 struct Sched { int ntm, ntn, ntiles, nkb, nchunks; };
 }  // namespace tcl2
 
-__global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
                                                                       const __grid_constant__ CUtensorMap map_blo,
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (trow & 7)) * 16));   // undo the 128B swizzle
-          split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
-          split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
         mbar_arrive(&bars->empty[s]);                          // this thread is done with the smem A tile
         mbar_wait(&bars->a_empty[s], ph ^ 1);
@@ -189,14 +189,17 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
       const float* Rrow = a.R ? a.R + (int64_t)bz * a.strideR + (int64_t)grow * a.ldr : nullptr;
       const int64_t yoff = (int64_t)bz * a.strideY + (int64_t)grow * a.ldy;
       const int64_t ytoff = (int64_t)bz * a.strideYt + grow;
-#pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {                   // not unrolled: keeps the kernel's code footprint small
         const int cb = n0 + ch * 32;
         if (cb >= a.nout || !row_ok) continue;
         const bool full = cb + 31 < a.nout;
         float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = racc[ch * 32 + j] * a.alpha;
+        switch (ch) {                                          // racc must stay statically indexed (registers)
+#define OG_COPY_CHUNK(CH_) case CH_: { _Pragma("unroll") for (int j = 0; j < 32; ++j) y[j] = racc[CH_ * 32 + j] * a.alpha; } break;
+          OG_COPY_CHUNK(0) OG_COPY_CHUNK(1) OG_COPY_CHUNK(2) default: OG_COPY_CHUNK(3)
+#undef OG_COPY_CHUNK
+        }
         if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (full || cb + j < a.nout) y[j] += __ldg(a.bias + cb + j);

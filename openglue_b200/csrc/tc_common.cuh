@@ -39,11 +39,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __noinline__ void mbar_timeout() {
+  printf("openglue_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) { printf("openglue_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n",
-                                        blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    if (++spins > (1u << 24)) mbar_timeout();
   }
 }
 
@@ -142,6 +147,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float r = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+// Same split for finite inputs in 5 ALU ops (cvt.rna.tf32 compiles to add / inf-test / select / mask = 4 ops
+// each): round-half-away on the magnitude bits.  Used in the inner loops of the converter / softmax warps.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  const float r = x - __uint_as_float(hi);
+  lo = (__float_as_uint(r) + 0x1000u) & 0xFFFFE000u;
 }
 
 // ----------------------------------------------------------------------------- host: tensor maps
