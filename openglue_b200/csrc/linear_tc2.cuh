@@ -11,7 +11,9 @@
 // and the pre-split B_hi / B_lo tiles (128 x 32 each) into a 4-deep 128B-swizzled smem ring.  The four
 // converter warps read their A row from smem (conflict-free through the swizzle), split it hi/lo in
 // registers and tcgen05.st it into a 4-deep TMEM ring, so A never occupies MMA-side smem bandwidth.
-// Warp roles: 0 = TMA, 1 = MMA issue (+TMEM alloc), 2-5 = A converters, 6-9 = accumulate + epilogue.
+// 16 warps: WG0 / WG1 = accumulate + epilogue for output columns [0,64) / [64,128) (64 fp32 accumulators per
+// thread, so 128 registers per thread suffice for every role), WG2 = A converters, warp 12 = TMA producer,
+// warp 13 = MMA issue + TMEM alloc.
 // One CTA per SM, static round-robin tile schedule (n fastest, so CTAs that run together share A in L2).
 #pragma once
 #include "tc_common.cuh"
@@ -24,20 +26,21 @@ constexpr int STAGES = 4;                 // smem ring (A raw + B hi + B lo) and
 constexpr int CHUNK_KB = 2;               // K blocks per accumulator chunk (K = 64)
 constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
-constexpr int THREADS = 320;
+constexpr int THREADS = 512;
 constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32)
 constexpr int COL_A = 256;
 
 struct __align__(8) Barriers {
   uint64_t full[STAGES], empty[STAGES], a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
+  float bias[BN], rscale[BN];           // per-tile epilogue vectors staged by the epilogue warps
 };
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2048;
 
 struct Sched { int ntm, ntn, ntiles, nkb, nchunks; };
 }  // namespace tcl2
 
-__global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
                                                                       const __grid_constant__ CUtensorMap map_blo,
@@ -47,19 +50,20 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
   extern __shared__ uint8_t og_tcl2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl2_smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction (setmaxnreg needs it)
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 129);       // 128 converter threads + MMA commit
       mbar_init(&bars->a_full[i], 128); mbar_init(&bars->a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 256); }
     fence_barrier_init();
     prefetch_tensormap(&map_a); prefetch_tensormap(&map_a2);
     prefetch_tensormap(&map_bhi); prefetch_tensormap(&map_blo);
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == 13) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -71,7 +75,8 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
     bz = t / (sc.ntn * sc.ntm);
   };
 
-  if (warp == 0) {
+  if (warp >= 12) {
+  if (warp == 12) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;                                              // global k-block counter (ring position)
@@ -92,7 +97,7 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_tf32(BM, BN);
     int it = 0, g = 0;                                         // k-block and chunk counters
@@ -126,7 +131,8 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp < 6) {
+  }
+  } else if (warp >= 8) {
     // ------------------------------------------------------------------ A converters: smem fp32 -> split -> TMEM
     const int q = warp & 3;
     const int trow = q * 32 + lane;
@@ -157,6 +163,8 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
     }
   } else {
     // ------------------------------------------------------------------ accumulate (RN, registers) + epilogue
+    const int half = warp >> 2;                                // 0: output columns [0,64), 1: [64,128) of the tile
+    constexpr int HN = BN / 2;
     const int q = warp & 3;
     const int trow = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -165,17 +173,17 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
     int g = 0;
     for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
       int m0, n0, bz; tile_coords(t, m0, n0, bz);
-      float racc[BN];
+      float racc[HN];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int j = 0; j < HN; ++j) racc[j] = 0.f;
       for (int c = 0; c < sc.nchunks; ++c, ++g) {
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_full[buf], gph);
         tc_fence_after();
 #pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = 0; ch < HN / 32; ++ch) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem + lane_base + buf * 128 + ch * 32, v);
+          tmem_ld_32x32(tmem + lane_base + buf * 128 + half * HN + ch * 32, v);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(v[j]);
@@ -189,79 +197,70 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
       const float* Rrow = a.R ? a.R + (int64_t)bz * a.strideR + (int64_t)grow * a.ldr : nullptr;
       const int64_t yoff = (int64_t)bz * a.strideY + (int64_t)grow * a.ldy;
       const int64_t ytoff = (int64_t)bz * a.strideYt + grow;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {                   // not unrolled: keeps the kernel's code footprint small
-        const int cb = n0 + ch * 32;
-        if (cb >= a.nout || !row_ok) continue;
-        const bool full = cb + 31 < a.nout;
-        float y[32];
-        switch (ch) {                                          // racc must stay statically indexed (registers)
-#define OG_COPY_CHUNK(CH_) case CH_: { _Pragma("unroll") for (int j = 0; j < 32; ++j) y[j] = racc[CH_ * 32 + j] * a.alpha; } break;
-          OG_COPY_CHUNK(0) OG_COPY_CHUNK(1) OG_COPY_CHUNK(2) default: OG_COPY_CHUNK(3)
-#undef OG_COPY_CHUNK
-        }
-        if (a.bias) {
+      // stage this tile's bias / residual scale once (one element per thread) instead of 128 loads per thread
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // previous tile's readers (both halves) are done
+      if (half == 0) {
+        bars->bias[trow] = (a.bias && n0 + trow < a.nout) ? __ldg(a.bias + n0 + trow) : 0.f;
+        bars->rscale[trow] = (a.rscale && n0 + trow < a.nout) ? __ldg(a.rscale + n0 + trow) : 1.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (full || cb + j < a.nout) y[j] += __ldg(a.bias + cb + j);
-        }
-        if (a.relu) {
+        for (int g4 = 0; g4 < HN / 4; ++g4) {                  // 4 output columns at a time: only racc[] stays live
+          const int cl = half * HN + g4 * 4;                   // column inside the tile
+          const int cb = n0 + cl;
+          if (cb >= a.nout) continue;
+          const bool full = cb + 3 < a.nout;
+          const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[cl]);
+          float y[4] = {fmaf(racc[g4 * 4 + 0], a.alpha, bv.x), fmaf(racc[g4 * 4 + 1], a.alpha, bv.y),
+                        fmaf(racc[g4 * 4 + 2], a.alpha, bv.z), fmaf(racc[g4 * 4 + 3], a.alpha, bv.w)};
+          if (a.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
-        }
-        if (Rrow) {
-          if (full && vec_r) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(Rrow + cb + j);
-              if (a.rscale) {
-                y[j] = fmaf(__ldg(a.rscale + cb + j), r.x, y[j]); y[j + 1] = fmaf(__ldg(a.rscale + cb + j + 1), r.y, y[j + 1]);
-                y[j + 2] = fmaf(__ldg(a.rscale + cb + j + 2), r.z, y[j + 2]); y[j + 3] = fmaf(__ldg(a.rscale + cb + j + 3), r.w, y[j + 3]);
-              } else { y[j] += r.x; y[j + 1] += r.y; y[j + 2] += r.z; y[j + 3] += r.w; }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
-              const float rv = Rrow[cb + j];
-              y[j] = a.rscale ? fmaf(__ldg(a.rscale + cb + j), rv, y[j]) : (y[j] + rv);
-            }
+            for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
           }
-        }
-        if (a.Y) {
-          if (full && vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(a.Y + yoff + cb + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (cb + j < a.nout) a.Y[yoff + cb + j] = y[j];
-          }
-        }
-        if (a.Yt) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (full || cb + j < a.nout) a.Yt[ytoff + (int64_t)(cb + j) * a.ldyt] = y[j];
-        }
-        if (a.Yhi || a.Ythi) {
-          uint32_t yh[32], yl[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) split_tf32(y[j], yh[j], yl[j]);
-          if (a.Yhi) {
-            if (full && vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                *reinterpret_cast<uint4*>(a.Yhi + yoff + cb + j) = make_uint4(yh[j], yh[j + 1], yh[j + 2], yh[j + 3]);
-                *reinterpret_cast<uint4*>(a.Ylo + yoff + cb + j) = make_uint4(yl[j], yl[j + 1], yl[j + 2], yl[j + 3]);
-              }
+          if (Rrow) {
+            const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl]);
+            if (full && vec_r) {
+              const float4 r = *reinterpret_cast<const float4*>(Rrow + cb);
+              y[0] = fmaf(sv.x, r.x, y[0]); y[1] = fmaf(sv.y, r.y, y[1]); y[2] = fmaf(sv.z, r.z, y[2]); y[3] = fmaf(sv.w, r.w, y[3]);
             } else {
+              const float svv[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
-                a.Yhi[yoff + cb + j] = __uint_as_float(yh[j]); a.Ylo[yoff + cb + j] = __uint_as_float(yl[j]);
-              }
+              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) y[j] = fmaf(svv[j], Rrow[cb + j], y[j]);
             }
           }
-          if (a.Ythi) {
+          if (a.Y) {
+            if (full && vec_ok) *reinterpret_cast<float4*>(a.Y + yoff + cb) = make_float4(y[0], y[1], y[2], y[3]);
+            else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (full || cb + j < a.nout) {
-              const int64_t o = ytoff + (int64_t)(cb + j) * a.ldyt;
-              a.Ythi[o] = __uint_as_float(yh[j]); a.Ytlo[o] = __uint_as_float(yl[j]);
+              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) a.Y[yoff + cb + j] = y[j];
+            }
+          }
+          if (a.Yt) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (cb + j < a.nout) a.Yt[ytoff + (int64_t)(cb + j) * a.ldyt] = y[j];
+          }
+          if (a.Yhi || a.Ythi) {
+            uint32_t yh[4], yl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32(y[j], yh[j], yl[j]);
+            if (a.Yhi) {
+              if (full && vec_ok) {
+                *reinterpret_cast<uint4*>(a.Yhi + yoff + cb) = make_uint4(yh[0], yh[1], yh[2], yh[3]);
+                *reinterpret_cast<uint4*>(a.Ylo + yoff + cb) = make_uint4(yl[0], yl[1], yl[2], yl[3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (cb + j < a.nout) {
+                  a.Yhi[yoff + cb + j] = __uint_as_float(yh[j]); a.Ylo[yoff + cb + j] = __uint_as_float(yl[j]);
+                }
+              }
+            }
+            if (a.Ythi) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) {
+                const int64_t o = ytoff + (int64_t)(cb + j) * a.ldyt;
+                a.Ythi[o] = __uint_as_float(yh[j]); a.Ytlo[o] = __uint_as_float(yl[j]);
+              }
             }
           }
         }
@@ -270,7 +269,7 @@ __global__ void __maxnreg__(200) linear_tc2_kernel(const __grid_constant__ CUten
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc<tcl2::TMEM_COLS>(tmem); }
+  if (warp == 13) { tc_fence_after(); tmem_dealloc<tcl2::TMEM_COLS>(tmem); }
 }
 
 inline bool linear_tc2_eligible(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb) {

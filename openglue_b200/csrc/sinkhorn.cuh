@@ -54,47 +54,97 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+// --- shared-memory row ring fed by bulk async copies (TMA 1-D): decouples HBM latency from the math ---
+constexpr int SINK_SLOTS = 2;             // rows in flight per warp (plus the one being processed in registers)
+
+__device__ __forceinline__ uint32_t sink_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sink_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sink_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sink_row_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sink_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sink_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sink_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sink_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(sink_smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 template <int V>
 __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a) {
-  extern __shared__ __align__(16) float og_sink_smem[];
-  float* v_s = og_sink_smem;                         // [mpad]   v_j, j = 0..m (m = dustbin column)
-  float* red = og_sink_smem + a.mpad;                // [SINK_WARPS][mpad]
+  extern __shared__ __align__(128) float og_sink_smem[];
+  constexpr int SLOT = 128 * V;                        // floats per ring slot (one padded row)
+  float* v_s = og_sink_smem;                           // [mpad]   v_j, j = 0..m (m = dustbin column)
+  float* red = og_sink_smem + a.mpad;                  // [SINK_WARPS][mpad]
+  float* ring = red + SINK_WARPS * a.mpad;             // [SINK_WARPS][SINK_SLOTS][SLOT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SINK_WARPS * SINK_SLOTS * SLOT);   // [SINK_WARPS][SINK_SLOTS]
   const int b = blockIdx.x / a.SP, strip = blockIdx.x % a.SP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = a.n, m = a.m;
   const int r0 = strip * a.rows_per_strip;
   const int r1 = min(r0 + a.rows_per_strip, n + 1);
+  const int r1_real = min(r1, n);                      // rows that exist in memory (the dustbin row does not)
   const float* __restrict__ Sb = a.S + (int64_t)b * a.strideS;
   const bool unit_reg = (a.reg == 1.0f);
   const float dz = unit_reg ? __ldg(a.dustbin) : __fdiv_rn(__ldg(a.dustbin), a.reg);   // Z = M / reg
   const float a_reg = expf(a.norm), a_last = expf(a.log_a_last);
+  const uint32_t row_bytes = (uint32_t)(((m + 3) / 4) * 16);      // <= 4 * lds: stays inside the padded row
+  float* my_ring = ring + warp * SINK_SLOTS * SLOT;
+  uint64_t* my_bars = bars + warp * SINK_SLOTS;
 
+  if (lane == 0) {
+    for (int sl = 0; sl < SINK_SLOTS; ++sl) sink_mbar_init(&my_bars[sl]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int j = tid; j <= m; j += blockDim.x) v_s[j] = 0.f;
   __syncthreads();
 
-  auto load_row = [&](int row, float4 (&z)[V]) {
+  uint32_t issued = 0, consumed = 0;                   // per-warp ring counters (real rows only)
+  auto prefetch_first = [&]() {                        // first SINK_SLOTS rows of this warp's strip share
+    if (lane == 0) {
+      for (int sl = 0; sl < SINK_SLOTS; ++sl) {
+        const int row = r0 + warp + sl * SINK_WARPS;
+        if (row < r1_real) { sink_row_copy(my_ring + (issued % SINK_SLOTS) * SLOT, Sb + (int64_t)row * a.lds, row_bytes, &my_bars[issued % SINK_SLOTS]); }
+        if (row < r1_real) ++issued;
+      }
+    }
+  };
+  // fetch row `row` of this warp into registers; refill the slot with the row SINK_SLOTS ahead
+  auto take_row = [&](int row, float4 (&z)[V]) {
     if (row < n) {
-      const float4* src = reinterpret_cast<const float4*>(Sb + (int64_t)row * a.lds);
+      const uint32_t sl = consumed % SINK_SLOTS, ph = (consumed / SINK_SLOTS) & 1;
+      sink_mbar_wait(&my_bars[sl], ph);
+      const float4* src = reinterpret_cast<const float4*>(my_ring + sl * SLOT);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const int idx = lane + 32 * k;
-        z[k] = (4 * idx < m) ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        z[k] = (4 * idx < m) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
-  };
-  auto scale_row = [&](int row, float4 (&z)[V]) {     // Z = M / reg; the dustbin row is constant
-    if (row >= n) {
+      ++consumed;
+      __syncwarp();                                    // every lane has its part of the row in registers
+      const int nxt = row + SINK_SLOTS * SINK_WARPS;
+      if (lane == 0 && nxt < r1_real) {
+        sink_row_copy(my_ring + sl * SLOT, Sb + (int64_t)nxt * a.lds, row_bytes, &my_bars[sl]);
+        ++issued;
+      }
+      if (!unit_reg) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
+          z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
+        }
+      }
+    } else {                                           // the dustbin row is the constant dustbin score
 #pragma unroll
       for (int k = 0; k < V; ++k) z[k] = make_float4(dz, dz, dz, dz);
-    } else if (!unit_reg) {
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
-        z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
-      }
     }
   };
 
+  prefetch_first();
   for (int it = 0; it < a.iters; ++it) {
     float4 cacc[V];
 #pragma unroll
@@ -102,13 +152,9 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
     float cacc_m = 0.f;
     const float v_m = v_s[m];
 
-    float4 z[V], zn[V];
-    int row = r0 + warp;
-    if (row < r1) load_row(row, z);
-    for (; row < r1; row += SINK_WARPS) {
-      const int nxt = row + SINK_WARPS;
-      if (nxt < r1) load_row(nxt, zn);               // prefetch: next row's loads fly during this row's math
-      scale_row(row, z);
+    for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
+      float4 z[V];
+      take_row(row, z);
       // t = z + v, masked; row max
       const float t_m = dz + v_m;                    // dustbin column entry of this row
       float mx = t_m;
@@ -143,9 +189,8 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
         cacc[k].z = fmaf(z[k].z, w_i, cacc[k].z); cacc[k].w = fmaf(z[k].w, w_i, cacc[k].w);
       }
       cacc_m = fmaf(e_m, w_i, cacc_m);
-#pragma unroll
-      for (int k = 0; k < V; ++k) z[k] = zn[k];
     }
+    prefetch_first();                                 // next sweep's (or the final pass's) first rows fly during the reduction
     // warp -> CTA
     float* myred = red + warp * a.mpad;
 #pragma unroll
@@ -178,10 +223,9 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
   // final pass: scores = Z + u + v - norm   (optimal_transport.py:28, superglue.py:111)
   {
     const float v_m = v_s[m];
-    float4 z[V];
     for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
-      load_row(row, z);
-      scale_row(row, z);
+      float4 z[V];
+      take_row(row, z);
       float u_i = 0.f;
       if (a.iters > 0) {
         if (lane == 0) u_i = a.u[(int64_t)b * (n + 1) + row];
@@ -222,7 +266,8 @@ inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
   if (p->mpad < 128 * p->V) {                      // v_s is read as float4 up to column 128 V - 1
     // only columns < m are ever used, but the smem reads must stay in bounds
   }
-  p->smem = (size_t)(1 + SINK_WARPS) * (size_t)std::max(p->mpad, 128 * p->V) * sizeof(float);
+  p->smem = ((size_t)(1 + SINK_WARPS) * (size_t)std::max(p->mpad, 128 * p->V) + (size_t)SINK_WARPS * SINK_SLOTS * 128 * p->V) * sizeof(float) +
+            (size_t)SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128;
   return OG_OK;
 }
 
@@ -238,7 +283,8 @@ inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream)
   static bool attr_set = false;
   if (!attr_set) {                       // largest request of this instantiation: m = 128 V  =>  mpad = 128 V + 4
     OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((1 + SINK_WARPS) * (128 * V + 4) * sizeof(float))));
+                                 (int)(((1 + SINK_WARPS) * (128 * V + 4) + SINK_WARPS * SINK_SLOTS * 128 * V) * sizeof(float) +
+                                       SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128)));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};

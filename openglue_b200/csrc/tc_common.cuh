@@ -140,6 +140,12 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// ----------------------------------------------------------------------------- register budget per warpgroup
+// One CTA = 3 warpgroups of 4 warps; the register file is partitioned per SM sub-partition, so each
+// warpgroup contributes one warp per partition.  Data-movement warpgroups hand registers to the math one.
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ----------------------------------------------------------------------------- tf32 split
 // x = hi + lo (+ <= 2^-23 |x|):  hi = rna_tf32(x), lo = rna_tf32(x - hi).  Both are tf32-exact, so the
 // tensor core's own truncation of the low mantissa bits never bites.
