@@ -9,9 +9,10 @@
 //   O_i  = P_i . V_i      A = P_i hi/lo in TMEM, B = V_i^T hi/lo tiles (TMA, smem), fresh accumulator
 //   acc  = acc * exp(m_{i-1} - m_i) + O_i      in registers of the softmax threads
 // Every contraction is three tf32 MMAs (lo.hi + hi.lo + hi.hi) with fp32 accumulation in TMEM.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = softmax /
-// correction / epilogue.  S/P and O are double buffered in TMEM so the tensor pipe works on block
-// i+1 while the softmax threads handle block i.
+// Warp roles (12 warps): warpgroups 0 and 1 = softmax / correction, alternating key blocks (WG g owns blocks
+// g, g+2, ... with its own S/P and O buffers in TMEM and its own online-softmax state; the two states are
+// merged once at the end), warp 8 = TMA producer, warp 9 = MMA issuer (+ TMEM alloc).  While one warpgroup is in its exp/split phase
+// the tensor pipe works on the other's QK^T / PV, so TMEM round trips and MUFU latency are hidden twice over.
 //
 // Operand layouts in HBM (written by the projection GEMM's epilogue, csrc/linear_tc.cuh):
 //   Q        fp32  [rows, ldq]            keypoint-major, head h = columns [h*Dh, (h+1)*Dh)
@@ -33,7 +34,7 @@ struct TcAttnArgs {
 namespace tca {
 constexpr int BM = 128, BNK = 64;               // queries per CTA, keys per block
 constexpr int STAGES = 3;
-constexpr int THREADS = 192;
+constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
 // TMEM columns:  Q_hi [0,64)  Q_lo [64,128)  SP_j [128+128j, +128) = {S / P_hi: 64, P_lo: 64}  O_j [384+64j, +64)
 constexpr int COL_QHI = 0, COL_QLO = 64, COL_SP = 128, COL_O = 384;
@@ -41,7 +42,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct __align__(8) Barriers {
   uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  uint64_t q_ready, s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t q_ready, s_full[2], p_full[2], o_full[2], o_empty[2], all_done;
   uint32_t tmem_base;
 };
 template <int DH> __host__ __device__ constexpr int k_stage_bytes() { return 2 * BNK * DH * 4; }        // hi + lo
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   uint8_t* sV = smem + STAGES * k_stage_bytes<DH>();
   Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<DH>());
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform (setmaxnreg)
+  const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (a.nk + BNK - 1) / BNK;
 
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
     mbar_init(&bars->q_ready, 128);
+    mbar_init(&bars->all_done, 1);
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 128);
       mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 128);
@@ -87,15 +90,16 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
     prefetch_tensormap(&map_vhi); prefetch_tensormap(&map_vlo);
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       const int krow0 = b * a.nk;                   // K rows of this batch item
       const int vrow = b * a.d + h * DH;            // V^T rows (channels) of this (batch, head)
       for (int i = 0; i < nblk; ++i) {
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc_qk = make_idesc_tf32(BM, BNK);
     const uint32_t idesc_pv = make_idesc_tf32(BM, DH);
@@ -126,10 +130,10 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
       mbar_wait(&bars->k_full[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH>()), klo = khi + K_HALF;
         const uint32_t d_s = tmem + COL_SP + 128 * j;
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < DH / 8; ++kk) {
           const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
@@ -152,11 +156,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_wait(&bars->p_full[j], jph);
       mbar_wait(&bars->o_empty[j], jph ^ 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH>()), vlo = vhi + V_HALF;
         const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
         const uint32_t d_o = tmem + COL_O + 64 * j;
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < BNK / 8; ++kk) {
           const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
@@ -166,18 +170,23 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         }
         umma_commit(&bars->v_empty[s]);
         umma_commit(&bars->o_full[j]);
+        if (i == nblk - 1) umma_commit(&bars->all_done);   // every MMA (hence every smem read) of this CTA has retired
       }
       __syncwarp();
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int g = warp >> 2;                         // warpgroup: owns key blocks g, g+2, ... and TMEM buffers SP_g, O_g
     const int qd = warp & 3;
     const int trow = qd * 32 + lane;
     const int grow = q0 + trow;
     const bool row_ok = grow < a.nq;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const uint32_t sp = tmem + lane_base + COL_SP + 128 * g;
+    const uint32_t op = tmem + lane_base + COL_O + 64 * g;
 
-    {   // Q row -> split -> TMEM (A operand of every QK^T)
+    if (g == 0) {   // Q row -> split -> TMEM (A operand of every QK^T)
       const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH;
 #pragma unroll
       for (int c0 = 0; c0 < DH; c0 += 32) {
@@ -203,36 +212,32 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     // is used consistently for p = 2^(s*c1 - mc) (one FFMA: the product is exact inside the fma, only the small
     // difference is rounded) and for the block-to-block correction 2^(mc_old - mc_new).
     const float c1 = a.scale * LOG2E;
-    float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, prev_corr = 0.f, next_corr = 0.f;
+    float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, corr_prev = 0.f;
 
-    auto fold_o = [&](int i, float corr) {        // acc = acc * corr + O_i
-      const int j = i & 1, jph = (i >> 1) & 1;
-      mbar_wait(&bars->o_full[j], jph);
+    auto fold_o = [&](int t, float corr) {           // acc = acc * corr + O of this warpgroup's t-th block
+      mbar_wait(&bars->o_full[g], t & 1);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < DH; c0 += 32) {
         uint32_t o[32];
-        tmem_ld_32x32(tmem + lane_base + COL_O + 64 * j + c0, o);
+        tmem_ld_32x32(op + c0, o);
         tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(acc[c0 + c], corr, __uint_as_float(o[c]));
       }
       tc_fence_before();
-      mbar_arrive(&bars->o_empty[j]);
+      mbar_arrive(&bars->o_empty[g]);
     };
 
-    // iteration i: softmax of block i (i < nblk), then fold of O_{i-1} (i >= 1); one inlined copy of each
+    int t = 0;                                       // index of the block within this warpgroup's sequence
 #pragma unroll 1
-    for (int i = 0; i <= nblk; ++i) {
-      if (i < nblk) {
-      const int j = i & 1, jph = (i >> 1) & 1;
-      const uint32_t sp = tmem + lane_base + COL_SP + 128 * j;
+    for (int i = g; i < nblk; i += 2, ++t) {
+      if (t >= 1) fold_o(t - 1, corr_prev);          // frees O_g well before the tensor pipe needs it again
       const int kbase = i * BNK;
-      mbar_wait(&bars->s_full[j], jph);
+      mbar_wait(&bars->s_full[g], t & 1);
       tc_fence_after();
-      const bool tail = kbase + BNK > a.nk;                          // last block only: mask keys >= nk
-      // pass A: block max.  The chunk loops are deliberately NOT unrolled: the per-block code must stay
-      // resident in the instruction cache (the fully unrolled first version spent 25% of its issue slots in no_inst).
+      const bool tail = kbase + BNK > a.nk;          // last block only: mask keys >= nk
+      // pass A: block max (chunk loops not unrolled: small code, and only one 32-column chunk live at a time)
       float mx = -CUDART_INF_F;
 #pragma unroll 1
       for (int c0 = 0; c0 < BNK; c0 += 32) {
@@ -246,11 +251,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
 #pragma unroll
         for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
       }
-      const float m_new = fmaxf(m_run, mx);                          // raw logits (scale > 0 commutes with max)
+      const float m_new = fmaxf(m_run, mx);          // raw logits (scale > 0 commutes with max)
       const float mc = m_new * c1;
-      const float corr = ex2_approx(mc_run - mc);                    // 2^(-inf) = 0 on the first block
+      const float corr = ex2_approx(mc_run - mc);    // 2^(-inf) = 0 on the first block
       // pass B: p = 2^(s*c1 - mc), split, back to TMEM (P_hi over S, P_lo beside it)
-      float rs = 0.f;
+      float r0 = 0.f, r1 = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < BNK; c0 += 32) {
         uint32_t s[32], lo[32];
@@ -260,7 +265,6 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
 #pragma unroll
           for (int c = 0; c < 32; ++c) if (kbase + c0 + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
         }
-        float r0 = 0.f, r1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), c1, -mc));
@@ -269,32 +273,45 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
           split_tf32_fast(p0, s[c], lo[c]);
           split_tf32_fast(p1, s[c + 1], lo[c + 1]);
         }
-        rs += r0 + r1;
         tmem_st_32x32(sp + c0, s);
         tmem_st_32x32(sp + 64 + c0, lo);
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[j]);
-      l_run = fmaf(l_run, corr, rs);
+      mbar_arrive(&bars->p_full[g]);
+      l_run = fmaf(l_run, corr, r0 + r1);
       m_run = m_new; mc_run = mc;
-      next_corr = corr;
-      }
-      if (i >= 1) fold_o(i - 1, prev_corr);
-      prev_corr = next_corr;
+      corr_prev = corr;
     }
+    if (t >= 1) fold_o(t - 1, corr_prev);
 
-    if (row_ok) {
-      const float inv = 1.f / l_run;
+    // ---- merge the two warpgroups' partial softmax states (the K/V ring is idle by now: reuse it)
+    float* mrg = reinterpret_cast<float*>(smem) + trow * 67;          // 67-float row stride: conflict-free
+    if (g == 1) {
+      mbar_wait(&bars->all_done, 0);                 // the ring may only be overwritten once the tensor pipe is done with it
+      mrg[0] = mc_run; mrg[1] = l_run;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) mrg[2 + c] = acc[c];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (g == 0 && row_ok) {
+      const float mcb = mrg[0], lb = mrg[1];
+      const float mm = fmaxf(mc_run, mcb);
+      const float fa = ex2_approx(mc_run - mm), fb = ex2_approx(mcb - mm);   // mcb = -inf (no odd block) -> fb = 0
+      const float inv = 1.f / fmaf(l_run, fa, lb * fb);
       float* orow = a.out + (int64_t)b * a.strideo + (int64_t)grow * a.ldo + h * DH;
 #pragma unroll
-      for (int c = 0; c < DH; c += 4)
-        *reinterpret_cast<float4*>(orow + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+      for (int c = 0; c < DH; c += 4) {
+        float4 o;
+        o.x = fmaf(acc[c], fa, mrg[2 + c] * fb) * inv;         o.y = fmaf(acc[c + 1], fa, mrg[3 + c] * fb) * inv;
+        o.z = fmaf(acc[c + 2], fa, mrg[4 + c] * fb) * inv;     o.w = fmaf(acc[c + 3], fa, mrg[5 + c] * fb) * inv;
+        *reinterpret_cast<float4*>(orow + c) = o;
+      }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc<tca::TMEM_COLS>(tmem); }
+  if (warp == 9) { tc_fence_after(); tmem_dealloc<tca::TMEM_COLS>(tmem); }
 }
 
 // khi/klo: [batch*nk, ldk];  vthi/vtlo: [batch*d, ldvt]

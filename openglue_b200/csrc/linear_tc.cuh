@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(tcl::THREADS) linear_tc_kernel(const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       const int brow = n0 + bz * a.b_rows_per_batch;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % B_STAGES, ph = (kb / B_STAGES) & 1;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(tcl::THREADS) linear_tc_kernel(const __grid_co
       mbar_wait(&bars->b_full[bs], bph);
       mbar_wait(&bars->a_full[as], aph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t bhi = smem_u32(sB + (bs * 2 + 0) * TILE_BYTES), blo = smem_u32(sB + (bs * 2 + 1) * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {

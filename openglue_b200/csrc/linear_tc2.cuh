@@ -33,7 +33,8 @@ constexpr int COL_A = 256;
 struct __align__(8) Barriers {
   uint64_t full[STAGES], empty[STAGES], a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
-  float bias[BN], rscale[BN];           // per-tile epilogue vectors staged by the epilogue warps
+  alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
+  alignas(16) float rscale[BN];
 };
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2048;
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   if (warp >= 12) {
   if (warp == 12) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;                                              // global k-block counter (ring position)
       for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
         int m0, n0, bz; tile_coords(t, m0, n0, bz);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
           mbar_wait(&bars->full[s], ph);                       // B tiles landed
           mbar_wait(&bars->a_full[s], ph);                     // A split written to TMEM
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + TILE_BYTES), blo = bhi + TILE_BYTES;
             const uint32_t d = tmem + buf * 128;
 #pragma unroll

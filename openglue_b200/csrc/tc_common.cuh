@@ -13,6 +13,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ----------------------------------------------------------------------------- single-lane election
+// elect.sync tells ptxas that exactly one lane runs the guarded region, so operands of the uniform-datapath
+// instructions (UTCHMMA, UTMALDG, UTCBAR) move to uniform registers without per-operand "waterfall" loops
+// (with `if (lane == 0)` the MMA-issue warp spent ~40 SASS instructions per tcgen05.mma and became the bottleneck).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
