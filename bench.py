@@ -181,7 +181,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='C3', choices=sorted(BASELINE_CONFIGS))
     ap.add_argument('--pairs-per-gpu', type=int, default=None)
-    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'fp32'), choices=['fp32', 'tf32x3'])
+    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'tf32x3'), choices=['fp32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     wl = dict(BASELINE_CONFIGS[args.workload])
@@ -339,7 +339,10 @@ def main():
         'roofline': {'kernel': 'fused attention (self layer: %d sequences x %d heads, %d x %d, Dh=%d)' % (nb, H, n, n, d // H),
                      'bound': 'tensor', 'achieved': attn_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                      'frac': attn_tflops / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 burst',
-                     'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops},
+                     'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops,
+                     # the kernel runs 3 tf32 MMAs per algorithmic product (fp32-grade accuracy is part of the contract);
+                     # tf32 dense rate = half the bf16 rate, so its own ceiling is bf16_peak / 6
+                     'frac_of_3xtf32_ceiling': attn_tflops / (peaks['bf16_tflops'] / 6.0) if args.precision == 'tf32x3' else None},
         'roofline_sinkhorn': {'kernel': 'sinkhorn (%d pairs, %d iterations, one launch)' % (batch, iters), 'bound': 'hbm',
                               'achieved': sink_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                               'frac': sink_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source'],

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       if (elect_one()) {
         const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH>()), klo = khi + K_HALF;
         const uint32_t d_s = tmem + COL_SP + 128 * j;
-#pragma unroll 1
+#pragma unroll
         for (int kk = 0; kk < DH / 8; ++kk) {
           const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH>()), vlo = vhi + V_HALF;
         const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
         const uint32_t d_o = tmem + COL_O + 64 * j;
-#pragma unroll 1
+#pragma unroll
         for (int kk = 0; kk < BNK / 8; ++kk) {
           const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);

@@ -54,7 +54,8 @@ def _gnn_params(num_stages: int, d: int) -> nn.Module:
 class SuperGlue(nn.Module):
     """B200-native matching core behind the reference's module API.
 
-    Extra (optional) config keys, ignored by the reference: ``precision`` ('fp32' | 'tf32x3'),
+    Extra (optional) config keys, ignored by the reference: ``precision`` ('tf32x3' (default): tcgen05 tensor
+    cores with error-compensated tf32, | 'fp32': CUDA-core FFMA everywhere),
     ``match_threshold`` (used by :class:`MatchingCore`).
     """
 
@@ -97,7 +98,7 @@ class SuperGlue(nn.Module):
 
     # ------------------------------------------------------------------ weights
     def _precision(self) -> int:
-        return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3}[self.config.get('precision', 'fp32')]
+        return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3}[self.config.get('precision', 'tf32x3')]
 
     def og_config(self) -> _cabi.OgConfig:
         return _cabi.make_config(self.config, self.config.get('match_threshold', 0.2), self._precision())

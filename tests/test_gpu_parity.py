@@ -123,7 +123,8 @@ def test_forward_matches_reference_c1(golden, name):
     (2, 256, 1100, dict(descriptor_dim=64, num_stages=1, num_iters=15, reg=0.5, use_offset=True,
                         residual=False), 'flat'),                                     # V=16 path, reg != 1
 ])
-def test_forward_matches_oracle(batch, n, m, kw, family):
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+def test_forward_matches_oracle(batch, n, m, kw, family, precision):
     cfg = default_config(**kw)
     sd = synthetic_state_dict(cfg, seed=3)
     data = synthetic_pairs(batch, n, m, cfg['descriptor_dim'], cfg['positional_encoding']['side_info_size'],
@@ -131,7 +132,7 @@ def test_forward_matches_oracle(batch, n, m, kw, family):
     ref = O.run(sd, cfg, data, 0.2)
     ref64 = O.run(sd, cfg, data, 0.2, dtype=torch.float64)
     bound = max(TOL, 2 * float((ref['scores'].double() - ref64['scores']).abs().max()))
-    model = _model(cfg, sd)
+    model = _model(cfg, sd, precision)
     res = MatchingCore(model, 0.2)(_to_dev(data), want_scores=True)
     assert (res['scores'].cpu().double() - ref64['scores']).abs().max() <= bound
     check_matches(res, ref, ref64['scores'], bound)
@@ -259,7 +260,7 @@ def test_headline_shape_properties():
     cfg = default_config(num_iters=100)
     sd = synthetic_state_dict(cfg, seed=0)
     data = synthetic_pairs(2, 2048, 2048, 256, 1, family='planted', seed=1234)
-    model = _model(cfg, sd)
+    model = _model(cfg, sd, 'tf32x3')
     core = MatchingCore(model, 0.2)
     res = core(_to_dev(data), want_scores=True)
     s = res['scores'].double()
