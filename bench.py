@@ -114,8 +114,9 @@ def time_oracle(cfg, n, m, reps, family='planted'):
     sd = synthetic_state_dict(cfg, seed=0)
     data = synthetic_pairs(1, n, m, cfg['descriptor_dim'], cfg['positional_encoding']['side_info_size'],
                            family=family, seed=1234)
-    default_threads = torch.get_num_threads()
-    cands = sorted({t for t in (8, 16, 32, default_threads) if t <= max(default_threads, 8)})
+    default_threads = torch.get_num_threads()             # torchrun pins OMP_NUM_THREADS=1: sweep by core count instead
+    ncpu = os.cpu_count() or 8
+    cands = sorted({t for t in (8, 16, 32, 64, default_threads) if t <= ncpu})
     best_t, best = default_threads, float('inf')
     for t in cands:
         torch.set_num_threads(t)

@@ -15,9 +15,15 @@
 // thread, so 128 registers per thread suffice for every role), WG2 = A converters, warp 12 = TMA producer,
 // warp 13 = MMA issue + TMEM alloc.
 // One CTA per SM, static round-robin tile schedule (n fastest, so CTAs that run together share A in L2).
+// Thread-block clusters of CL CTAs along M share the B tile: every CTA TMA-loads 1/CL of its rows with
+// .multicast::cluster into all CL shared memories, cutting B's L2->SM traffic by CL (measured before: the
+// kernel moved 6-7.5 TB/s out of L2, i.e. it was L2-bound with B = 2/3 of the bytes).  Stage recycling across
+// CTAs: a producer tells its peers when its own stage is free and issues only when all peers said the same.
 #pragma once
 #include "tc_common.cuh"
 #include "linear_tc.cuh"     // TcLinearArgs
+#include <algorithm>
+#include <stdlib.h>
 
 namespace og {
 namespace tcl2 {
@@ -30,17 +36,18 @@ constexpr int THREADS = 512;
 constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32)
 constexpr int COL_A = 256;
 
-struct __align__(8) Barriers {
-  uint64_t full[STAGES], empty[STAGES], a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2];
+struct __align__(16) Barriers {
+  uint64_t full[STAGES], empty[STAGES], a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2], peer_free[STAGES];
   uint32_t tmem_base;
   alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
   alignas(16) float rscale[BN];
 };
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2048;
 
-struct Sched { int ntm, ntn, ntiles, nkb, nchunks; };
+struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of CL m-tiles; ngroups = ntn * ntmg * batch
 }  // namespace tcl2
 
+template <int CL>
 __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
@@ -53,11 +60,14 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction (setmaxnreg needs it)
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int g_first = blockIdx.x / CL, g_stride = gridDim.x / CL;     // cluster index / number of clusters
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 129);       // 128 converter threads + MMA commit
       mbar_init(&bars->a_full[i], 128); mbar_init(&bars->a_empty[i], 1);
+      mbar_init(&bars->peer_free[i], CL > 1 ? CL - 1 : 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 256); }
     fence_barrier_init();
@@ -67,13 +77,15 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   if (warp == 13) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                            // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  // group tile t = CL consecutive m-tiles x one n-tile; this CTA takes m-tile number `crank` of the group
   auto tile_coords = [&](int t, int& m0, int& n0, int& bz) {
     n0 = (t % sc.ntn) * BN;
-    m0 = ((t / sc.ntn) % sc.ntm) * BM;
-    bz = t / (sc.ntn * sc.ntm);
+    m0 = (((t / sc.ntn) % sc.ntmg) * CL + (int)crank) * BM;
+    bz = t / (sc.ntn * sc.ntmg);
   };
 
   if (warp >= 12) {
@@ -81,20 +93,31 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;                                              // global k-block counter (ring position)
-      for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+      for (int t = g_first; t < sc.ngroups; t += g_stride) {
         int m0, n0, bz; tile_coords(t, m0, n0, bz);
         const int arow = bz * a.rows + m0;                     // batches are dense: row index into [batch*rows, K]
         const int brow = n0 + bz * a.b_rows_per_batch;
         for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&bars->empty[s], ph ^ 1);
+          mbar_wait(&bars->empty[s], ph ^ 1);                  // my consumers released stage s
+          if (CL > 1) {
+#pragma unroll
+            for (uint32_t r = 0; r < (uint32_t)CL; ++r) if (r != crank) mbar_arrive_remote(&bars->peer_free[s], r);
+            mbar_wait(&bars->peer_free[s], ph);                // ... and so did every peer's (they will receive my B slice)
+          }
           mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
           uint8_t* dst = smem + s * STAGE_BYTES;
           const int k = kb * BK;
           if (k < a.k1) tma_load_2d(dst, &map_a, &bars->full[s], k, arow);
           else          tma_load_2d(dst, &map_a2, &bars->full[s], k - a.k1, arow);
-          tma_load_2d(dst + TILE_BYTES, &map_bhi, &bars->full[s], k, brow);
-          tma_load_2d(dst + 2 * TILE_BYTES, &map_blo, &bars->full[s], k, brow);
+          if (CL > 1) {                                        // my 128/CL rows of B_hi / B_lo go to every CTA of the cluster
+            constexpr int SL = BN / CL;
+            tma_load_2d_mcast(dst + TILE_BYTES + crank * SL * 128, &map_bhi, &bars->full[s], k, brow + crank * SL, (uint16_t)((1u << CL) - 1));
+            tma_load_2d_mcast(dst + 2 * TILE_BYTES + crank * SL * 128, &map_blo, &bars->full[s], k, brow + crank * SL, (uint16_t)((1u << CL) - 1));
+          } else {
+            tma_load_2d(dst + TILE_BYTES, &map_bhi, &bars->full[s], k, brow);
+            tma_load_2d(dst + 2 * TILE_BYTES, &map_blo, &bars->full[s], k, brow);
+          }
         }
       }
     }
@@ -102,7 +125,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_tf32(BM, BN);
     int it = 0, g = 0;                                         // k-block and chunk counters
-    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+    for (int t = g_first; t < sc.ngroups; t += g_stride) {
       for (int c = 0; c < sc.nchunks; ++c, ++g) {
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_empty[buf], gph ^ 1);
@@ -139,7 +162,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     const int trow = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     int it = 0;
-    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+    for (int t = g_first; t < sc.ngroups; t += g_stride) {
       for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&bars->full[s], ph);
@@ -172,7 +195,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     const bool vec_ok = (a.ldy % 4 == 0) && (a.strideY % 4 == 0);
     const bool vec_r = a.R && (a.ldr % 4 == 0) && (a.strideR % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
     int g = 0;
-    for (int t = blockIdx.x; t < sc.ntiles; t += gridDim.x) {
+    for (int t = g_first; t < sc.ngroups; t += g_stride) {
       int m0, n0, bz; tile_coords(t, m0, n0, bz);
       float racc[HN];
 #pragma unroll
@@ -270,6 +293,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                            // no CTA leaves while a peer may still write its smem / barriers
   if (warp == 13) { tc_fence_after(); tmem_dealloc<tcl2::TMEM_COLS>(tmem); }
 }
 
@@ -280,8 +304,9 @@ inline bool linear_tc2_eligible(const TcLinearArgs& a, const float* Bhi, const f
   return true;
 }
 
-inline int linear_tc2_launch(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
-                             cudaStream_t stream) {
+template <int CL>
+inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
+                                cudaStream_t stream) {
   using namespace tcl2;
   const int K = a.k1 + a.k2;
   CUtensorMap ma, ma2, mhi, mlo;
@@ -290,22 +315,51 @@ inline int linear_tc2_launch(const TcLinearArgs& a, const float* Bhi, const floa
   if ((rc = tc::make_tmap_2d(&ma, a.A, arows, (uint64_t)a.k1, (uint64_t)a.lda, BM)) != OG_OK) return rc;
   if (a.A2) { if ((rc = tc::make_tmap_2d(&ma2, a.A2, arows, (uint64_t)a.k2, (uint64_t)a.lda2, BM)) != OG_OK) return rc; }
   else ma2 = ma;
-  if ((rc = tc::make_tmap_2d(&mhi, Bhi, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN)) != OG_OK) return rc;
-  if ((rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mhi, Bhi, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   Sched sc;
-  sc.ntm = cdiv(a.rows, BM); sc.ntn = cdiv(a.nout, BN); sc.ntiles = sc.ntm * sc.ntn * a.batch;
+  sc.ntmg = cdiv(cdiv(a.rows, BM), CL); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
   sc.nkb = cdiv(K, BK); sc.nchunks = cdiv(sc.nkb, CHUNK_KB);
   const int sms = device_info().ok ? device_info().sm_count : 148;
-  const int grid = sc.ntiles < sms ? sc.ntiles : sms;
-  linear_tc2_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, ma2, mhi, mlo, a, sc);
-  OG_LAUNCH_CHECK("linear_tc2_kernel");
+  const int nclusters = std::min(sc.ngroups, sms / CL);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<CL>, ma, ma2, mhi, mlo, a, sc));
   launch_counter()++;
   return OG_OK;
+}
+
+// cluster size along M (B-tile multicast): OG_TC_CLUSTER env (1, 2 or 4) overrides the default
+inline int linear_tc2_cluster_size() {
+  static int cl = [] {
+    const char* e = getenv("OG_TC_CLUSTER");
+    int v = e ? atoi(e) : 2;
+    return (v == 1 || v == 2 || v == 4) ? v : 2;
+  }();
+  return cl;
+}
+
+inline int linear_tc2_launch(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
+                             cudaStream_t stream) {
+  int cl = linear_tc2_cluster_size();
+  while (cl > 1 && cdiv(a.rows, tcl2::BM) < cl) cl >>= 1;              // tiny problems: no point in phantom m-tiles
+  switch (cl) {
+    case 4: return linear_tc2_launch_cl<4>(a, Bhi, Blo, ldb, b_total_rows, stream);
+    case 2: return linear_tc2_launch_cl<2>(a, Bhi, Blo, ldb, b_total_rows, stream);
+    default: return linear_tc2_launch_cl<1>(a, Bhi, Blo, ldb, b_total_rows, stream);
+  }
 }
 
 }  // namespace og
