@@ -26,14 +26,21 @@
 #include <stdlib.h>
 
 namespace og {
+#ifdef OG_TRACE
+// debug build only (scripts/trace_gemm.py): per-k-block event timestamps of CTA 0
+__device__ long long og_trace_buf[8 * 256];
+#define OG_TRACE_EVT(ev, idx) do { if (blockIdx.x == 0 && (idx) < 256) og_trace_buf[(ev) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define OG_TRACE_EVT(ev, idx) do { } while (0)
+#endif
 namespace tcl2 {
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 4;                 // smem ring (A raw + B hi + B lo) and TMEM A ring
+constexpr int STAGES = 3;                 // smem ring (A raw + B hi + B lo); the TMEM A ring has the same depth
 constexpr int CHUNK_KB = 2;               // K blocks per accumulator chunk (K = 64)
 constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int THREADS = 512;
-constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32)
+constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32), s < STAGES
 constexpr int COL_A = 256;
 
 struct __align__(16) Barriers {
@@ -42,7 +49,9 @@ struct __align__(16) Barriers {
   alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
   alignas(16) float rscale[BN];
 };
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2048;
+constexpr int OUT_TILE = 128 * 32 * 4;    // one staged [128 rows x 32 cols] output chunk (16 KB)
+constexpr int OUT_BYTES = 2 * 2 * OUT_TILE;  // 2 epilogue warpgroups x 2 buffers
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + 2048;
 
 struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of CL m-tiles; ngroups = ntn * ntmg * batch
 }  // namespace tcl2
@@ -52,12 +61,16 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
                                                                       const __grid_constant__ CUtensorMap map_blo,
-                                                                      TcLinearArgs a, tcl2::Sched sc) {
+                                                                      const __grid_constant__ CUtensorMap map_y,
+                                                                      const __grid_constant__ CUtensorMap map_yhi,
+                                                                      const __grid_constant__ CUtensorMap map_ylo,
+                                                                      TcLinearArgs a, tcl2::Sched sc, int y_tma) {
   using namespace tcl2;
   using namespace tc;
   extern __shared__ uint8_t og_tcl2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl2_smem_raw) + 1023) & ~uintptr_t(1023));
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* s_out = smem + STAGES * STAGE_BYTES;                          // [2 warpgroups][2 buffers][16 KB]
+  Barriers* bars = reinterpret_cast<Barriers*>(s_out + OUT_BYTES);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction (setmaxnreg needs it)
   const int lane = threadIdx.x & 31;
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
@@ -100,6 +113,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&bars->empty[s], ph ^ 1);                  // my consumers released stage s
+          OG_TRACE_EVT(0, it);
           if (CL > 1) {
 #pragma unroll
             for (uint32_t r = 0; r < (uint32_t)CL; ++r) if (r != crank) mbar_arrive_remote(&bars->peer_free[s], r);
@@ -134,8 +148,10 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         for (int kb = c * CHUNK_KB; kb < kb_end; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&bars->full[s], ph);                       // B tiles landed
+          OG_TRACE_EVT(3, it);
           mbar_wait(&bars->a_full[s], ph);                     // A split written to TMEM
           tc_fence_after();
+          OG_TRACE_EVT(4, it);
           if (elect_one()) {
             const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + TILE_BYTES), blo = bhi + TILE_BYTES;
             const uint32_t d = tmem + buf * 128;
@@ -166,6 +182,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
       for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&bars->full[s], ph);
+        if (warp == 8 && lane == 0) OG_TRACE_EVT(1, it);
         const uint8_t* arow = smem + s * STAGE_BYTES + trow * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -183,6 +200,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->a_full[s]);
+        if (warp == 8 && lane == 0) OG_TRACE_EVT(2, it);
       }
     }
   } else {
@@ -192,7 +210,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     const int q = warp & 3;
     const int trow = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const bool vec_ok = (a.ldy % 4 == 0) && (a.strideY % 4 == 0);
+    const int wg_tid = threadIdx.x & 127;
+    int nstore = 0;                                            // staged stores issued by this warpgroup so far
     const bool vec_r = a.R && (a.ldr % 4 == 0) && (a.strideR % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
     int g = 0;
     for (int t = g_first; t < sc.ngroups; t += g_stride) {
@@ -204,6 +223,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_full[buf], gph);
         tc_fence_after();
+        if (warp == 0 && lane == 0) OG_TRACE_EVT(5, g);
 #pragma unroll
         for (int ch = 0; ch < HN / 32; ++ch) {
           uint32_t v[32];
@@ -214,6 +234,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         }
         tc_fence_before();
         mbar_arrive(&bars->acc_empty[buf]);
+        if (warp == 0 && lane == 0) OG_TRACE_EVT(6, g);
       }
       // ---- epilogue for this tile (overlaps the next tile's first chunks)
       const int grow = m0 + trow;
@@ -228,68 +249,89 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         bars->rscale[trow] = (a.rscale && n0 + trow < a.nout) ? __ldg(a.rscale + n0 + trow) : 1.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (row_ok) {
 #pragma unroll
-        for (int g4 = 0; g4 < HN / 4; ++g4) {                  // 4 output columns at a time: only racc[] stays live
-          const int cl = half * HN + g4 * 4;                   // column inside the tile
-          const int cb = n0 + cl;
-          if (cb >= a.nout) continue;
-          const bool full = cb + 3 < a.nout;
-          const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[cl]);
-          float y[4] = {fmaf(racc[g4 * 4 + 0], a.alpha, bv.x), fmaf(racc[g4 * 4 + 1], a.alpha, bv.y),
-                        fmaf(racc[g4 * 4 + 2], a.alpha, bv.z), fmaf(racc[g4 * 4 + 3], a.alpha, bv.w)};
-          if (a.relu) {
+      for (int cc = 0; cc < HN / 32; ++cc) {                   // 32-column chunks of this warpgroup's half
+        const int cl = half * HN + cc * 32;                    // column inside the tile
+        const int cb = n0 + cl;
+        if (cb >= a.nout) continue;                            // uniform across the warpgroup
+        float y[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-          }
-          if (Rrow) {
-            const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl]);
-            if (full && vec_r) {
-              const float4 r = *reinterpret_cast<const float4*>(Rrow + cb);
-              y[0] = fmaf(sv.x, r.x, y[0]); y[1] = fmaf(sv.y, r.y, y[1]); y[2] = fmaf(sv.z, r.z, y[2]); y[3] = fmaf(sv.w, r.w, y[3]);
-            } else {
-              const float svv[4] = {sv.x, sv.y, sv.z, sv.w};
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[cl + j]);
+          y[j] = fmaf(racc[cc * 32 + j], a.alpha, bv.x);         y[j + 1] = fmaf(racc[cc * 32 + j + 1], a.alpha, bv.y);
+          y[j + 2] = fmaf(racc[cc * 32 + j + 2], a.alpha, bv.z); y[j + 3] = fmaf(racc[cc * 32 + j + 3], a.alpha, bv.w);
+        }
+        if (a.relu) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) y[j] = fmaf(svv[j], Rrow[cb + j], y[j]);
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
+        if (Rrow && row_ok) {
+          if (cb + 31 < a.nout && vec_r) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(Rrow + cb + j);
+              const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl + j]);
+              y[j] = fmaf(sv.x, r.x, y[j]); y[j + 1] = fmaf(sv.y, r.y, y[j + 1]);
+              y[j + 2] = fmaf(sv.z, r.z, y[j + 2]); y[j + 3] = fmaf(sv.w, r.w, y[j + 3]);
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cb + j < a.nout) y[j] = fmaf(bars->rscale[cl + j], Rrow[cb + j], y[j]);
           }
+        }
+        // transposed outputs: for a fixed column the 32 lanes write 32 consecutive rows (already coalesced)
+        if (a.Yt && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (cb + j < a.nout) a.Yt[ytoff + (int64_t)(cb + j) * a.ldyt] = y[j];
+        }
+        // row-major outputs: the chunk is staged in 128B-swizzled smem and written by one TMA store (full 128-byte
+        // segments per row, clipped to the tensor bounds); measured before: per-thread row stores took ~10K of the
+        // ~16K cycles per tile.
+        auto stage_store = [&](const CUtensorMap* map, const uint32_t (&v)[32]) {
+          uint8_t* buf = s_out + (half * 2 + (nstore & 1)) * OUT_TILE;
+          if (wg_tid == 0) tma_store_wait_read<1>();           // the store that last read this buffer is done with it
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          uint8_t* dst = buf + trow * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(dst + ((c ^ (trow & 7)) * 16)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          fence_proxy_async();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (wg_tid == 0) { tma_store_3d(map, buf, cb, m0, bz); tma_store_commit(); }
+          ++nstore;
+        };
+        if (y_tma) {
           if (a.Y) {
-            if (full && vec_ok) *reinterpret_cast<float4*>(a.Y + yoff + cb) = make_float4(y[0], y[1], y[2], y[3]);
-            else {
+            uint32_t v[32];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) a.Y[yoff + cb + j] = y[j];
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(y[j]);
+            stage_store(&map_y, v);
           }
-          if (a.Yt) {
+          if (a.Yhi) {
+            uint32_t yh[32], yl[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (cb + j < a.nout) a.Yt[ytoff + (int64_t)(cb + j) * a.ldyt] = y[j];
+            for (int j = 0; j < 32; ++j) split_tf32(y[j], yh[j], yl[j]);
+            stage_store(&map_yhi, yh);
+            stage_store(&map_ylo, yl);
           }
-          if (a.Yhi || a.Ythi) {
-            uint32_t yh[4], yl[4];
+        } else if (row_ok) {                                   // unaligned row pitch: plain stores
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split_tf32(y[j], yh[j], yl[j]);
-            if (a.Yhi) {
-              if (full && vec_ok) {
-                *reinterpret_cast<uint4*>(a.Yhi + yoff + cb) = make_uint4(yh[0], yh[1], yh[2], yh[3]);
-                *reinterpret_cast<uint4*>(a.Ylo + yoff + cb) = make_uint4(yl[0], yl[1], yl[2], yl[3]);
-              } else {
+          for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
+            if (a.Y) a.Y[yoff + cb + j] = y[j];
+            if (a.Yhi) { uint32_t h, l; split_tf32(y[j], h, l); a.Yhi[yoff + cb + j] = __uint_as_float(h); a.Ylo[yoff + cb + j] = __uint_as_float(l); }
+          }
+        }
+        if (a.Ythi && row_ok) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (cb + j < a.nout) {
-                  a.Yhi[yoff + cb + j] = __uint_as_float(yh[j]); a.Ylo[yoff + cb + j] = __uint_as_float(yl[j]);
-                }
-              }
-            }
-            if (a.Ythi) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) if (cb + j < a.nout) {
-                const int64_t o = ytoff + (int64_t)(cb + j) * a.ldyt;
-                a.Ythi[o] = __uint_as_float(yh[j]); a.Ytlo[o] = __uint_as_float(yl[j]);
-              }
-            }
+          for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
+            uint32_t h, l; split_tf32(y[j], h, l);
+            const int64_t o = ytoff + (int64_t)(cb + j) * a.ldyt;
+            a.Ythi[o] = __uint_as_float(h); a.Ytlo[o] = __uint_as_float(l);
           }
         }
       }
     }
+    if (wg_tid == 0) tma_store_wait_all<0>();                  // smem must outlive the last store's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -317,6 +359,15 @@ inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const f
   else ma2 = ma;
   if ((rc = tc::make_tmap_2d(&mhi, Bhi, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
   if ((rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
+  // row-major outputs go out through TMA stores when their rows are 16-byte aligned
+  CUtensorMap my = ma, myh = ma, myl = ma;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int y_tma = (a.Y || a.Yhi) && a.ldy % 4 == 0 && a.strideY % 4 == 0 && (!a.Y || al16(a.Y)) && (!a.Yhi || (al16(a.Yhi) && al16(a.Ylo)));
+  if (y_tma) {
+    if (a.Y && (rc = tc::make_tmap_3d(&my, a.Y, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+    if (a.Yhi && (rc = tc::make_tmap_3d(&myh, a.Yhi, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+    if (a.Yhi && (rc = tc::make_tmap_3d(&myl, a.Ylo, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -336,17 +387,20 @@ inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const f
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<CL>, ma, ma2, mhi, mlo, a, sc));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<CL>, ma, ma2, mhi, mlo, my, myh, myl, a, sc, y_tma));
   launch_counter()++;
   return OG_OK;
 }
 
-// cluster size along M (B-tile multicast): OG_TC_CLUSTER env (1, 2 or 4) overrides the default
+// Cluster size along M (B-tile multicast).  Measured on B200 (profiles/README.md): 2-CTA clusters are ~5% slower and
+// 4-CTA clusters 2.8x slower than no clusters - the kernel is bound by the depth of its smem ring (bytes in flight per
+// SM), which multicast does not change, and the cross-CTA stage handshake adds latency.  Default 1; OG_TC_CLUSTER=2|4
+// keeps the path testable.
 inline int linear_tc2_cluster_size() {
   static int cl = [] {
     const char* e = getenv("OG_TC_CLUSTER");
-    int v = e ? atoi(e) : 2;
-    return (v == 1 || v == 2 || v == 4) ? v : 2;
+    int v = e ? atoi(e) : 1;
+    return (v == 1 || v == 2 || v == 4) ? v : 1;
   }();
   return cl;
 }

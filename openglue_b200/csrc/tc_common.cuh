@@ -84,6 +84,15 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensor
       : "memory");
 }
 
+// TMA store: a 128B-swizzled smem tile -> global (3-D map [batch, rows, cols]: clips at the batch boundary)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ----------------------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -223,6 +232,23 @@ inline int make_tmap_2d(CUtensorMap* map, const float* base, uint64_t rows, uint
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OG_ECUDA, "cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return OG_OK;
+}
+
+// 3-D fp32 tensor [batch, rows, cols] (row stride ld, batch stride bstride, in floats); box = 32 cols x box_rows x 1.
+inline int make_tmap_3d(CUtensorMap* map, const float* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint64_t bstride, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(OG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (batch <= 1 || bstride == 0) { batch = 1; bstride = rows * ld; }
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * sizeof(float), bstride * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OG_ECUDA, "cuTensorMapEncodeTiled (3d) failed (%d)", (int)r);
   return OG_OK;
 }
 
