@@ -327,6 +327,10 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and args.workload == 'C3' and batch == 16 and args.precision == 'tf32x3':
+        traffic = json.load(open(tpath))     # ncu dram bytes per launch, captured at exactly these shapes
     fl = flops_per_pair(n, m, d, stages, s_dim)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
@@ -339,14 +343,16 @@ def main():
         'clocks': clocks,
         'roofline': {'kernel': 'fused attention (self layer: %d sequences x %d heads, %d x %d, Dh=%d)' % (nb, H, n, n, d // H),
                      'bound': 'tensor', 'achieved': attn_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                     'frac': attn_tflops / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 burst',
+                     'frac': attn_tflops / peaks['bf16_tflops'],
+                     'traffic': traffic.get('attention_tc_self_32seq_2048', {}).get('bytes'), 'peak_source': peaks['source'] + ' bf16 burst',
                      'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops,
                      # the kernel runs 3 tf32 MMAs per algorithmic product (fp32-grade accuracy is part of the contract);
                      # tf32 dense rate = half the bf16 rate, so its own ceiling is bf16_peak / 6
                      'frac_of_3xtf32_ceiling': attn_tflops / (peaks['bf16_tflops'] / 6.0) if args.precision == 'tf32x3' else None},
         'roofline_sinkhorn': {'kernel': 'sinkhorn (%d pairs, %d iterations, one launch)' % (batch, iters), 'bound': 'hbm',
                               'achieved': sink_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                              'frac': sink_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source'],
+                              'frac': sink_gbs / peaks['hbm_gbs'],
+                              'traffic': traffic.get('sinkhorn_16pairs_2048_100it', {}).get('bytes'), 'peak_source': peaks['source'],
                               'ms_per_launch': ms_sink, 'bytes_per_launch': sinkhorn_bytes_per_pair(n, m, iters) * batch},
         'flops_per_pair': fl['total'],
         'end_to_end_tensor_frac': value / world * fl['total'] / (peaks['bf16_tflops_sustained'] * 1e12),
