@@ -21,6 +21,7 @@
 #pragma once
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace og {
 
@@ -45,12 +46,16 @@ struct __align__(8) Barriers {
   uint64_t q_ready, s_full[2], p_full[2], o_full[2], o_empty[2], all_done;
   uint32_t tmem_base;
 };
-template <int DH> __host__ __device__ constexpr int k_stage_bytes() { return 2 * BNK * DH * 4; }        // hi + lo
-template <int DH> __host__ __device__ constexpr int v_stage_bytes() { return 2 * DH * BNK * 4; }
-template <int DH> __host__ __device__ constexpr int smem_bytes() { return 1024 + STAGES * (k_stage_bytes<DH>() + v_stage_bytes<DH>()) + 512; }
+// CG = 1: one CTA per 128 queries.  CG = 2: a CTA pair (cta_group::2) per 256 queries; every MMA spans both SMs
+// (M = 256) and each CTA stages only half of the K rows / V^T channels of a block.
+template <int DH, int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * DH * 4; }        // hi + lo
+template <int DH, int CG> __host__ __device__ constexpr int v_stage_bytes() { return 2 * (DH / CG) * BNK * 4; }
+template <int DH, int CG> __host__ __device__ constexpr int smem_bytes() {
+  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512;
+}
 }  // namespace tca
 
-template <int DH>
+template <int DH, int CG>
 __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_khi,
                                                                        const __grid_constant__ CUtensorMap map_klo,
                                                                        const __grid_constant__ CUtensorMap map_vhi,
@@ -59,19 +64,21 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   using namespace tca;
   using namespace tc;
   static_assert(DH == 32 || DH == 64, "head_dim 32 or 64");
-  constexpr int KBLK = BNK * 128;                 // bytes of one [64 keys x 32 ch] K block
-  constexpr int VBLK = DH * 128;                  // bytes of one [DH ch x 32 keys] V^T block
+  constexpr int KROWS = BNK / CG, VCH = DH / CG;  // K rows / V^T channels of a block staged by THIS CTA
+  constexpr int KBLK = KROWS * 128;               // bytes of one [KROWS keys x 32 ch] K block
+  constexpr int VBLK = VCH * 128;                 // bytes of one [VCH ch x 32 keys] V^T block
   constexpr int K_HALF = (DH / 32) * KBLK;        // hi (or lo) part of a K stage
   constexpr int V_HALF = 2 * VBLK;
 
   extern __shared__ uint8_t og_tca_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tca_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
-  uint8_t* sV = smem + STAGES * k_stage_bytes<DH>();
-  Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<DH>());
+  uint8_t* sV = smem + STAGES * k_stage_bytes<DH, CG>();
+  Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<DH, CG>());
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform (setmaxnreg)
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (a.nk + BNK - 1) / BNK;
 
@@ -80,21 +87,25 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_init(&bars->k_full[i], 1); mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
-    mbar_init(&bars->q_ready, 128);
+    mbar_init(&bars->q_ready, 128 * CG);             // CG = 2: the leader's barriers also count the peer's threads
     mbar_init(&bars->all_done, 1);
     for (int j = 0; j < 2; ++j) {
-      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 128);
-      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 128);
+      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 128 * CG);
+      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 128 * CG);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
     prefetch_tensormap(&map_vhi); prefetch_tensormap(&map_vlo);
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (CG == 2) cluster_sync_all();                 // both CTAs' barriers exist before anything signals them
+  if (warp == 9) { if (CG == 2) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base); else tmem_alloc<TMEM_COLS>(&bars->tmem_base); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  // signal a barrier that lives in the leader CTA (local arrive for CG = 1 / the leader itself)
+  auto arrive_leader = [&](uint64_t* bar) { if (CG == 1 || crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); };
+  auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); };
 
   if (warp >= 8) {
   if (warp == 8) {
@@ -105,44 +116,59 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       for (int i = 0; i < nblk; ++i) {
         const int s = i % STAGES, ph = (i / STAGES) & 1;
         mbar_wait(&bars->k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->k_full[s], k_stage_bytes<DH>());
-        uint8_t* kd = sK + s * k_stage_bytes<DH>();
+        if (crank == 0) mbar_arrive_expect_tx(&bars->k_full[s], CG * k_stage_bytes<DH, CG>());   // both CTAs' bytes land on the leader's barrier
+        uint8_t* kd = sK + s * k_stage_bytes<DH, CG>();
+        const int kr = krow0 + i * BNK + (int)crank * KROWS;          // my half of the block's keys
 #pragma unroll
         for (int cb = 0; cb < DH / 32; ++cb) {
-          tma_load_2d(kd + cb * KBLK, &map_khi, &bars->k_full[s], h * DH + cb * 32, krow0 + i * BNK);
-          tma_load_2d(kd + K_HALF + cb * KBLK, &map_klo, &bars->k_full[s], h * DH + cb * 32, krow0 + i * BNK);
+          if (CG == 2) {
+            tma_load_2d_pair(kd + cb * KBLK, &map_khi, &bars->k_full[s], h * DH + cb * 32, kr);
+            tma_load_2d_pair(kd + K_HALF + cb * KBLK, &map_klo, &bars->k_full[s], h * DH + cb * 32, kr);
+          } else {
+            tma_load_2d(kd + cb * KBLK, &map_khi, &bars->k_full[s], h * DH + cb * 32, kr);
+            tma_load_2d(kd + K_HALF + cb * KBLK, &map_klo, &bars->k_full[s], h * DH + cb * 32, kr);
+          }
         }
         mbar_wait(&bars->v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->v_full[s], v_stage_bytes<DH>());
-        uint8_t* vd = sV + s * v_stage_bytes<DH>();
+        if (crank == 0) mbar_arrive_expect_tx(&bars->v_full[s], CG * v_stage_bytes<DH, CG>());
+        uint8_t* vd = sV + s * v_stage_bytes<DH, CG>();
+        const int vr = vrow + (int)crank * VCH;                       // my half of the head's channels
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          tma_load_2d(vd + kb * VBLK, &map_vhi, &bars->v_full[s], i * BNK + kb * 32, vrow);
-          tma_load_2d(vd + V_HALF + kb * VBLK, &map_vlo, &bars->v_full[s], i * BNK + kb * 32, vrow);
+          if (CG == 2) {
+            tma_load_2d_pair(vd + kb * VBLK, &map_vhi, &bars->v_full[s], i * BNK + kb * 32, vr);
+            tma_load_2d_pair(vd + V_HALF + kb * VBLK, &map_vlo, &bars->v_full[s], i * BNK + kb * 32, vr);
+          } else {
+            tma_load_2d(vd + kb * VBLK, &map_vhi, &bars->v_full[s], i * BNK + kb * 32, vr);
+            tma_load_2d(vd + V_HALF + kb * VBLK, &map_vlo, &bars->v_full[s], i * BNK + kb * 32, vr);
+          }
         }
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_qk = make_idesc_tf32(BM, BNK);
-    const uint32_t idesc_pv = make_idesc_tf32(BM, DH);
+  } else if (warp == 9 && crank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only when paired)
+    const uint32_t idesc_qk = make_idesc_tf32(BM * CG, BNK);
+    const uint32_t idesc_pv = make_idesc_tf32(BM * CG, DH);
+    auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t id, uint32_t acc) {
+      if (CG == 2) umma_tf32_ts_pair(d, at, bd, id, acc); else umma_tf32_ts(d, at, bd, id, acc);
+    };
     auto issue_qk = [&](int i) {
       const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
       mbar_wait(&bars->k_full[s], ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH>()), klo = khi + K_HALF;
+        const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH, CG>()), klo = khi + K_HALF;
         const uint32_t d_s = tmem + COL_SP + 128 * j;
 #pragma unroll
         for (int kk = 0; kk < DH / 8; ++kk) {
           const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
-          umma_tf32_ts(d_s, tmem + COL_QLO + kk * 8, dhi, idesc_qk, kk ? 1u : 0u);
-          umma_tf32_ts(d_s, tmem + COL_QHI + kk * 8, dlo, idesc_qk, 1u);
-          umma_tf32_ts(d_s, tmem + COL_QHI + kk * 8, dhi, idesc_qk, 1u);
+          mma(d_s, tmem + COL_QLO + kk * 8, dhi, idesc_qk, kk ? 1u : 0u);
+          mma(d_s, tmem + COL_QHI + kk * 8, dlo, idesc_qk, 1u);
+          mma(d_s, tmem + COL_QHI + kk * 8, dhi, idesc_qk, 1u);
         }
-        umma_commit(&bars->k_empty[s]);
-        umma_commit(&bars->s_full[j]);
+        commit(&bars->k_empty[s]);
+        commit(&bars->s_full[j]);
       }
       __syncwarp();
     };
@@ -157,20 +183,20 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_wait(&bars->o_empty[j], jph ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH>()), vlo = vhi + V_HALF;
+        const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH, CG>()), vlo = vhi + V_HALF;
         const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
         const uint32_t d_o = tmem + COL_O + 64 * j;
 #pragma unroll
         for (int kk = 0; kk < BNK / 8; ++kk) {
           const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
           const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
-          umma_tf32_ts(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
-          umma_tf32_ts(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
-          umma_tf32_ts(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
+          mma(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
+          mma(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
+          mma(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
         }
-        umma_commit(&bars->v_empty[s]);
-        umma_commit(&bars->o_full[j]);
-        if (i == nblk - 1) umma_commit(&bars->all_done);   // every MMA (hence every smem read) of this CTA has retired
+        commit(&bars->v_empty[s]);
+        commit(&bars->o_full[j]);
+        if (i == nblk - 1) commit(&bars->all_done);   // every MMA (hence every smem read) of this CTA has retired
       }
       __syncwarp();
     }
@@ -202,7 +228,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->q_ready);
+      arrive_leader(&bars->q_ready);
     }
 
     float acc[DH];
@@ -226,7 +252,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(acc[c0 + c], corr, __uint_as_float(o[c]));
       }
       tc_fence_before();
-      mbar_arrive(&bars->o_empty[g]);
+      arrive_leader(&bars->o_empty[g]);
     };
 
     int t = 0;                                       // index of the block within this warpgroup's sequence
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars->p_full[g]);
+      arrive_leader(&bars->p_full[g]);
       l_run = fmaf(l_run, corr, r0 + r1);
       m_run = m_new; mc_run = mc;
       corr_prev = corr;
@@ -311,38 +337,54 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 9) { tc_fence_after(); tmem_dealloc<tca::TMEM_COLS>(tmem); }
+  if (CG == 2) cluster_sync_all();                 // the peer may still be reading my smem / signalling my barriers
+  if (warp == 9) { tc_fence_after(); if (CG == 2) tmem_dealloc_pair<tca::TMEM_COLS>(tmem); else tmem_dealloc<tca::TMEM_COLS>(tmem); }
 }
 
 // khi/klo: [batch*nk, ldk];  vthi/vtlo: [batch*d, ldvt]
-inline int attention_tc_launch(const TcAttnArgs& a, const float* khi, const float* klo, int64_t ldk, const float* vthi,
-                               const float* vtlo, int64_t ldvt, int head_dim, cudaStream_t stream) {
+template <int DH, int CG>
+inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const float* klo, int64_t ldk, const float* vthi,
+                                 const float* vtlo, int64_t ldvt, cudaStream_t stream) {
   using namespace tca;
   CUtensorMap mkh, mkl, mvh, mvl;
   int rc;
-  if ((rc = tc::make_tmap_2d(&mkh, khi, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK)) != OG_OK) return rc;
-  if ((rc = tc::make_tmap_2d(&mkl, klo, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK)) != OG_OK) return rc;
-  if ((rc = tc::make_tmap_2d(&mvh, vthi, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, head_dim)) != OG_OK) return rc;
-  if ((rc = tc::make_tmap_2d(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, head_dim)) != OG_OK) return rc;
-  dim3 grid(cdiv(a.nq, BM), a.num_heads, a.batch);
-#define OG_TCA_CASE(DH_)                                                                                      \
-  case DH_: {                                                                                                 \
-    static bool attr_set = false;                                                                             \
-    if (!attr_set) {                                                                                          \
-      OG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<DH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                   smem_bytes<DH_>()));                                                       \
-      attr_set = true;                                                                                        \
-    }                                                                                                         \
-    attention_tc_kernel<DH_><<<grid, THREADS, smem_bytes<DH_>(), stream>>>(mkh, mkl, mvh, mvl, a);            \
-  } break;
-  switch (head_dim) {
-    OG_TCA_CASE(32) OG_TCA_CASE(64)
-    default: return fail(OG_EUNSUPPORTED, "attention_tc: head_dim %d not in {32, 64}", head_dim);
+  if ((rc = tc::make_tmap_2d(&mkh, khi, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK / CG)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mkl, klo, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK / CG)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mvh, vthi, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<DH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<DH, CG>()));
+    attr_set = true;
   }
-#undef OG_TCA_CASE
-  OG_LAUNCH_CHECK("attention_tc_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(cdiv(a.nq, BM), CG) * CG, a.num_heads, a.batch);       // CG = 2: an odd last query block gets a phantom partner
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem_bytes<DH, CG>();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<DH, CG>, mkh, mkl, mvh, mvl, a));
   launch_counter()++;
   return OG_OK;
+}
+
+// OG_ATTN_PAIR=0 selects the single-CTA kernel (cross-check of the cta_group::2 path)
+inline int attention_tc_pair_mode() {
+  static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+inline int attention_tc_launch(const TcAttnArgs& a, const float* khi, const float* klo, int64_t ldk, const float* vthi,
+                               const float* vtlo, int64_t ldvt, int head_dim, cudaStream_t stream) {
+  const bool pair = attention_tc_pair_mode() != 0;
+  if (head_dim == 64) return pair ? attention_tc_launch_t<64, 2>(a, khi, klo, ldk, vthi, vtlo, ldvt, stream)
+                                  : attention_tc_launch_t<64, 1>(a, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  if (head_dim == 32) return pair ? attention_tc_launch_t<32, 2>(a, khi, klo, ldk, vthi, vtlo, ldvt, stream)
+                                  : attention_tc_launch_t<32, 1>(a, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  return fail(OG_EUNSUPPORTED, "attention_tc: head_dim %d not in {32, 64}", head_dim);
 }
 
 inline bool attention_tc_eligible(int head_dim, int64_t ldq, int64_t ldk, int64_t ldvt, int64_t ldo) {

@@ -105,6 +105,38 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one MMA spans two SMs (M = 256, each CTA holds half of B's N rows) ----
+// TMA load into MY smem that reports its bytes to the mbarrier at the same offset in the leader CTA (rank 0)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  uint32_t rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rbar) : "r"(smem_u32(bar)));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(rbar), "r"(c0), "r"(c1) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder) {   // the same warp in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+               ::"r"(smem_u32(smem_holder)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// commit -> arrive on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc] over the CTA pair (issued by the leader CTA only)
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder) {      // one full warp
