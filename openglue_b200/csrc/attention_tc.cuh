@@ -9,10 +9,9 @@
 //   O_i  = P_i . V_i      A = P_i hi/lo in TMEM, B = V_i^T hi/lo tiles (TMA, smem), fresh accumulator
 //   acc  = acc * exp(m_{i-1} - m_i) + O_i      in registers of the softmax threads
 // Every contraction is three tf32 MMAs (lo.hi + hi.lo + hi.hi) with fp32 accumulation in TMEM.
-// Warp roles (12 warps): warpgroups 0 and 1 = softmax / correction, alternating key blocks (WG g owns blocks
-// g, g+2, ... with its own S/P and O buffers in TMEM and its own online-softmax state; the two states are
-// merged once at the end), warp 8 = TMA producer, warp 9 = MMA issuer (+ TMEM alloc).  While one warpgroup is in its exp/split phase
-// the tensor pipe works on the other's QK^T / PV, so TMEM round trips and MUFU latency are hidden twice over.
+// Warp roles (12 warps): warpgroups 0 and 1 = softmax / correction, splitting every key block by columns (WG g:
+// logit columns [32g, 32g+32) and output channels [g*Dh/2, (g+1)*Dh/2); the half-row maxima are exchanged through
+// smem once per block), warp 8 = TMA producer, warp 9 = MMA issuer (+ TMEM alloc).
 //
 // Operand layouts in HBM (written by the projection GEMM's epilogue, csrc/linear_tc.cuh):
 //   Q        fp32  [rows, ldq]            keypoint-major, head h = columns [h*Dh, (h+1)*Dh)
@@ -51,7 +50,7 @@ struct __align__(8) Barriers {
 template <int DH, int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * DH * 4; }        // hi + lo
 template <int DH, int CG> __host__ __device__ constexpr int v_stage_bytes() { return 2 * (DH / CG) * BNK * 4; }
 template <int DH, int CG> __host__ __device__ constexpr int smem_bytes() {
-  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512;
+  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512 + 6 * 128 * 4;
 }
 }  // namespace tca
 
@@ -87,11 +86,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_init(&bars->k_full[i], 1); mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
-    mbar_init(&bars->q_ready, 128 * CG);             // CG = 2: the leader's barriers also count the peer's threads
+    mbar_init(&bars->q_ready, 8 * CG);               // one arrival per softmax warp (8 per CTA); CG = 2: the leader also counts the peer's
     mbar_init(&bars->all_done, 1);
     for (int j = 0; j < 2; ++j) {
-      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 128 * CG);
-      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 128 * CG);
+      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 8 * CG);
+      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
@@ -104,7 +103,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   // signal a barrier that lives in the leader CTA (local arrive for CG = 1 / the leader itself)
-  auto arrive_leader = [&](uint64_t* bar) { if (CG == 1 || crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); };
+  // (one lane per warp, after every lane of the warp has completed and fenced its own TMEM accesses)
+  auto arrive_leader = [&](uint64_t* bar) {
+    __syncwarp();
+    if (lane == 0) { if (CG == 1 || crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); }
+  };
   auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); };
 
   if (warp >= 8) {
@@ -203,136 +206,134 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int g = warp >> 2;                         // warpgroup: owns key blocks g, g+2, ... and TMEM buffers SP_g, O_g
+    // Two warpgroups share every key block: warpgroup g owns logit columns [32g, 32g+32) of the 64-key block and
+    // output channels [g*DH/2, (g+1)*DH/2).  Thread = one query row in both.  The row max of a block needs both
+    // halves: one smem exchange + one 256-thread named barrier per block.  This halves the softmax latency per
+    // block (the tensor pipe stalls whenever P_i is not ready within one QK + one PV of MMA time).
+    constexpr int HD = DH / 2;                       // output channels per warpgroup
+    const int g = warp >> 2;
     const int qd = warp & 3;
     const int trow = qd * 32 + lane;
     const int grow = q0 + trow;
     const bool row_ok = grow < a.nq;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const uint32_t sp = tmem + lane_base + COL_SP + 128 * g;
-    const uint32_t op = tmem + lane_base + COL_O + 64 * g;
+    float* xch = reinterpret_cast<float*>(bars + 1);                   // [2 parities][2 warpgroups][128] row maxima, then [2][128] sums
 
-    if (g == 0) {   // Q row -> split -> TMEM (A operand of every QK^T)
-      const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH;
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
+    {   // my half of the Q row -> split -> TMEM (A operand of every QK^T)
+      const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH + g * HD;
+      if constexpr (HD == 32) {
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
           split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
-        tmem_st_32x32(tmem + lane_base + COL_QHI + c0, hi);
-        tmem_st_32x32(tmem + lane_base + COL_QLO + c0, lo);
+        tmem_st_32x32(tmem + lane_base + COL_QHI + g * HD, hi);
+        tmem_st_32x32(tmem + lane_base + COL_QLO + g * HD, lo);
+      } else {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+        }
+        tmem_st_32x16(tmem + lane_base + COL_QHI + g * HD, hi);
+        tmem_st_32x16(tmem + lane_base + COL_QLO + g * HD, lo);
       }
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->q_ready);
     }
 
-    float acc[DH];
+    float acc[HD];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    for (int c = 0; c < HD; ++c) acc[c] = 0.f;
     // Online softmax in the exp2 domain.  c1 = scale*log2(e); mc = fl(m*c1) is the running max in that domain and
     // is used consistently for p = 2^(s*c1 - mc) (one FFMA: the product is exact inside the fma, only the small
     // difference is rounded) and for the block-to-block correction 2^(mc_old - mc_new).
     const float c1 = a.scale * LOG2E;
     float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, corr_prev = 0.f;
 
-    auto fold_o = [&](int t, float corr) {           // acc = acc * corr + O of this warpgroup's t-th block
-      mbar_wait(&bars->o_full[g], t & 1);
+    auto fold_o = [&](int i, float corr) {           // acc = acc * corr + my channels of O_i
+      const int j = i & 1, jph = (i >> 1) & 1;
+      mbar_wait(&bars->o_full[j], jph);
       tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
+      const uint32_t op = tmem + lane_base + COL_O + 64 * j + g * HD;
+      if constexpr (HD == 32) {
         uint32_t o[32];
-        tmem_ld_32x32(op + c0, o);
+        tmem_ld_32x32(op, o);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(acc[c0 + c], corr, __uint_as_float(o[c]));
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(acc[c], corr, __uint_as_float(o[c]));
+      } else {
+        uint32_t o[16];
+        tmem_ld_32x16(op, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], corr, __uint_as_float(o[c]));
       }
       tc_fence_before();
-      arrive_leader(&bars->o_empty[g]);
+      arrive_leader(&bars->o_empty[j]);
     };
 
-    int t = 0;                                       // index of the block within this warpgroup's sequence
 #pragma unroll 1
-    for (int i = g; i < nblk; i += 2, ++t) {
-      if (t >= 1) fold_o(t - 1, corr_prev);          // frees O_g well before the tensor pipe needs it again
-      const int kbase = i * BNK;
-      mbar_wait(&bars->s_full[g], t & 1);
+    for (int i = 0; i < nblk; ++i) {
+      const int j = i & 1, jph = (i >> 1) & 1;
+      const uint32_t sp = tmem + lane_base + COL_SP + 128 * j + 32 * g;      // my 32 columns of S_i / P_hi
+      const int kbase = i * BNK + 32 * g;
+      mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
-      const bool tail = kbase + BNK > a.nk;          // last block only: mask keys >= nk
-      // pass A: block max (chunk loops not unrolled: small code, and only one 32-column chunk live at a time)
-      float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BNK; c0 += 32) {
-        uint32_t s[32];
-        tmem_ld_32x32(sp + c0, s);
-        tmem_wait_ld();
-        if (tail) {
+      uint32_t s[32], lo[32];
+      tmem_ld_32x32(sp, s);
+      tmem_wait_ld();
+      if (kbase + 32 > a.nk) {                       // key tail (last block only): mask keys >= nk
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (kbase + c0 + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
-        }
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
+        for (int c = 0; c < 32; ++c) if (kbase + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
       }
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
+      xch[(j * 2 + g) * 128 + trow] = mx;            // exchange the half-row maxima
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[(j * 2 + (g ^ 1)) * 128 + trow]);
       const float m_new = fmaxf(m_run, mx);          // raw logits (scale > 0 commutes with max)
       const float mc = m_new * c1;
       const float corr = ex2_approx(mc_run - mc);    // 2^(-inf) = 0 on the first block
-      // pass B: p = 2^(s*c1 - mc), split, back to TMEM (P_hi over S, P_lo beside it)
       float r0 = 0.f, r1 = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BNK; c0 += 32) {
-        uint32_t s[32], lo[32];
-        tmem_ld_32x32(sp + c0, s);
-        tmem_wait_ld();
-        if (tail) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (kbase + c0 + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
-        }
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), c1, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), c1, -mc));
-          r0 += p0; r1 += p1;
-          split_tf32_fast(p0, s[c], lo[c]);
-          split_tf32_fast(p1, s[c + 1], lo[c + 1]);
-        }
-        tmem_st_32x32(sp + c0, s);
-        tmem_st_32x32(sp + 64 + c0, lo);
+      for (int c = 0; c < 32; c += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), c1, -mc));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), c1, -mc));
+        r0 += p0; r1 += p1;
+        split_tf32_fast(p0, s[c], lo[c]);
+        split_tf32_fast(p1, s[c + 1], lo[c + 1]);
       }
+      tmem_st_32x32(sp, s);                          // P_hi over S, P_lo beside it
+      tmem_st_32x32(sp + 64, lo);
       tmem_wait_st();
       tc_fence_before();
-      arrive_leader(&bars->p_full[g]);
-      l_run = fmaf(l_run, corr, r0 + r1);
+      arrive_leader(&bars->p_full[j]);
+      l_run = fmaf(l_run, corr, r0 + r1);            // partial row sum over my 32 columns (same max in both warpgroups)
       m_run = m_new; mc_run = mc;
+      // P_i is on its way; now fold O_{i-1} (computed with m_{i-1}: its correction is the one saved last iteration).
+      // Doing this AFTER the softmax keeps P_i off the critical path; O_{i-1}'s buffer is only needed again by PV_{i+1}.
+      if (i >= 1) fold_o(i - 1, corr_prev);
       corr_prev = corr;
     }
-    if (t >= 1) fold_o(t - 1, corr_prev);
+    fold_o(nblk - 1, corr_prev);
 
-    // ---- merge the two warpgroups' partial softmax states (the K/V ring is idle by now: reuse it)
-    float* mrg = reinterpret_cast<float*>(smem) + trow * 67;          // 67-float row stride: conflict-free
-    if (g == 1) {
-      mbar_wait(&bars->all_done, 0);                 // the ring may only be overwritten once the tensor pipe is done with it
-      mrg[0] = mc_run; mrg[1] = l_run;
-#pragma unroll
-      for (int c = 0; c < DH; ++c) mrg[2 + c] = acc[c];
-    }
+    // total row sum = sum of the two warpgroups' partial sums
+    float* xl = xch + 4 * 128;
+    xl[g * 128 + trow] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (g == 0 && row_ok) {
-      const float mcb = mrg[0], lb = mrg[1];
-      const float mm = fmaxf(mc_run, mcb);
-      const float fa = ex2_approx(mc_run - mm), fb = ex2_approx(mcb - mm);   // mcb = -inf (no odd block) -> fb = 0
-      const float inv = 1.f / fmaf(l_run, fa, lb * fb);
-      float* orow = a.out + (int64_t)b * a.strideo + (int64_t)grow * a.ldo + h * DH;
+    const float inv = 1.f / (l_run + xl[(g ^ 1) * 128 + trow]);
+    if (row_ok) {
+      float* orow = a.out + (int64_t)b * a.strideo + (int64_t)grow * a.ldo + h * DH + g * HD;
 #pragma unroll
-      for (int c = 0; c < DH; c += 4) {
-        float4 o;
-        o.x = fmaf(acc[c], fa, mrg[2 + c] * fb) * inv;         o.y = fmaf(acc[c + 1], fa, mrg[3 + c] * fb) * inv;
-        o.z = fmaf(acc[c + 2], fa, mrg[4 + c] * fb) * inv;     o.w = fmaf(acc[c + 3], fa, mrg[5 + c] * fb) * inv;
-        *reinterpret_cast<float4*>(orow + c) = o;
-      }
+      for (int c = 0; c < HD; c += 4)
+        *reinterpret_cast<float4*>(orow + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
     }
     tc_fence_before();
   }
@@ -371,9 +372,11 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
   return OG_OK;
 }
 
-// OG_ATTN_PAIR=0 selects the single-CTA kernel (cross-check of the cta_group::2 path)
+// OG_ATTN_PAIR=1 selects the cta_group::2 (CTA pair, M = 256) form.  It is parity-clean but measured ~15% slower than the
+// single-CTA form on B200 (profiles/README.md): the extra cross-CTA barrier hops per key block cost more than the halved
+// B-operand traffic and MMA count per SM give back.  Default 0.
 inline int attention_tc_pair_mode() {
-  static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 1; }();
+  static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 0; }();
   return v;
 }
 
