@@ -11,7 +11,7 @@
 // Every contraction is three tf32 MMAs (lo.hi + hi.lo + hi.hi) with fp32 accumulation in TMEM.
 // Warp roles (12 warps): warpgroups 0 and 1 = softmax / correction, splitting every key block by columns (WG g:
 // logit columns [32g, 32g+32) and output channels [g*Dh/2, (g+1)*Dh/2); the half-row maxima are exchanged through
-// smem once per block), warp 8 = TMA producer, warp 9 = MMA issuer (+ TMEM alloc).
+// smem once per block), warp 8 = TMA producer, warps 9 / 10 = MMA issuers for QK^T / P.V (warp 9 also owns TMEM).
 //
 // Operand layouts in HBM (written by the projection GEMM's epilogue, csrc/linear_tc.cuh):
 //   Q        fp32  [rows, ldq]            keypoint-major, head h = columns [h*Dh, (h+1)*Dh)
@@ -148,60 +148,69 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         }
       }
     }
-  } else if (warp == 9 && crank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only when paired)
+  } else if ((warp == 9 || warp == 10) && crank == 0) {
+    // ------------------------------------------------------------------ MMA issuers (leader CTA only when paired)
+    // Two issuing warps: measured (scripts/trace_attn.py), ONE thread needs ~40-47 cycles per tcgen05.mma while an
+    // M128 N64 K8 tf32 MMA occupies the tensor pipe for 32 - the issuing thread, not the pipe, paced the kernel.
+    // Warp 9 issues every QK^T, warp 10 every P.V; they only meet through mbarriers.
     const uint32_t idesc_qk = make_idesc_tf32(BM * CG, BNK);
     const uint32_t idesc_pv = make_idesc_tf32(BM * CG, DH);
     auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t id, uint32_t acc) {
       if (CG == 2) umma_tf32_ts_pair(d, at, bd, id, acc); else umma_tf32_ts(d, at, bd, id, acc);
     };
-    auto issue_qk = [&](int i) {
-      const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
-      mbar_wait(&bars->k_full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH, CG>()), klo = khi + K_HALF;
-        const uint32_t d_s = tmem + COL_SP + 128 * j;
+    if (warp == 9) {
+      mbar_wait(&bars->q_ready, 0);
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
+        OG_TRACE_EVT(0, i);
+        mbar_wait(&bars->k_full[s], ph);
+        if (i >= 2) mbar_wait(&bars->o_full[j], ((i - 2) >> 1) & 1);   // PV_{i-2} has consumed P_{i-2}: S/P buffer j is free
+        tc_fence_after();
+        OG_TRACE_EVT(1, i);
+        if (elect_one()) {
+          const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH, CG>()), klo = khi + K_HALF;
+          const uint32_t d_s = tmem + COL_SP + 128 * j;
 #pragma unroll
-        for (int kk = 0; kk < DH / 8; ++kk) {
-          const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
-          const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
-          mma(d_s, tmem + COL_QLO + kk * 8, dhi, idesc_qk, kk ? 1u : 0u);
-          mma(d_s, tmem + COL_QHI + kk * 8, dlo, idesc_qk, 1u);
-          mma(d_s, tmem + COL_QHI + kk * 8, dhi, idesc_qk, 1u);
+          for (int kk = 0; kk < DH / 8; ++kk) {
+            const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
+            const uint64_t dhi = make_sdesc_sw128(khi + off), dlo = make_sdesc_sw128(klo + off);
+            mma(d_s, tmem + COL_QLO + kk * 8, dhi, idesc_qk, kk ? 1u : 0u);
+            mma(d_s, tmem + COL_QHI + kk * 8, dlo, idesc_qk, 1u);
+            mma(d_s, tmem + COL_QHI + kk * 8, dhi, idesc_qk, 1u);
+          }
+          commit(&bars->k_empty[s]);
+          commit(&bars->s_full[j]);
         }
-        commit(&bars->k_empty[s]);
-        commit(&bars->s_full[j]);
+        __syncwarp();
       }
-      __syncwarp();
-    };
-    mbar_wait(&bars->q_ready, 0);
-    tc_fence_after();
-    issue_qk(0);
-    for (int i = 0; i < nblk; ++i) {
-      if (i + 1 < nblk) issue_qk(i + 1);            // keep the tensor pipe fed while block i is in softmax
-      const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1, jph = (i >> 1) & 1;
-      mbar_wait(&bars->v_full[s], ph);
-      mbar_wait(&bars->p_full[j], jph);
-      mbar_wait(&bars->o_empty[j], jph ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH, CG>()), vlo = vhi + V_HALF;
-        const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
-        const uint32_t d_o = tmem + COL_O + 64 * j;
+    } else {
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1, jph = (i >> 1) & 1;
+        OG_TRACE_EVT(2, i);
+        mbar_wait(&bars->v_full[s], ph);
+        mbar_wait(&bars->p_full[j], jph);
+        OG_TRACE_EVT(3, i);
+        mbar_wait(&bars->o_empty[j], jph ^ 1);
+        tc_fence_after();
+        OG_TRACE_EVT(4, i);
+        if (elect_one()) {
+          const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH, CG>()), vlo = vhi + V_HALF;
+          const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
+          const uint32_t d_o = tmem + COL_O + 64 * j;
 #pragma unroll
-        for (int kk = 0; kk < BNK / 8; ++kk) {
-          const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
-          const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
-          mma(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
-          mma(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
-          mma(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
+          for (int kk = 0; kk < BNK / 8; ++kk) {
+            const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
+            const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
+            mma(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
+            mma(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
+            mma(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
+          }
+          commit(&bars->v_empty[s]);
+          commit(&bars->o_full[j]);
+          if (i == nblk - 1) commit(&bars->all_done);
         }
-        commit(&bars->v_empty[s]);
-        commit(&bars->o_full[j]);
-        if (i == nblk - 1) commit(&bars->all_done);   // every MMA (hence every smem read) of this CTA has retired
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   } else {
@@ -276,6 +285,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       }
       tc_fence_before();
       arrive_leader(&bars->o_empty[j]);
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(7, i); // O_i folded
     };
 
 #pragma unroll 1
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       const int kbase = i * BNK + 32 * g;
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(5, i); // softmax: S_i observed
       uint32_t s[32], lo[32];
       tmem_ld_32x32(sp, s);
       tmem_wait_ld();
@@ -315,6 +326,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->p_full[j]);
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(6, i); // softmax: P_i handed over
       l_run = fmaf(l_run, corr, r0 + r1);            // partial row sum over my 32 columns (same max in both warpgroups)
       m_run = m_new; mc_run = mc;
       // P_i is on its way; now fold O_{i-1} (computed with m_{i-1}: its correction is the one saved last iteration).

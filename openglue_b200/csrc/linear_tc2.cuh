@@ -26,13 +26,6 @@
 #include <stdlib.h>
 
 namespace og {
-#ifdef OG_TRACE
-// debug build only (scripts/trace_gemm.py): per-k-block event timestamps of CTA 0
-__device__ long long og_trace_buf[8 * 256];
-#define OG_TRACE_EVT(ev, idx) do { if (blockIdx.x == 0 && (idx) < 256) og_trace_buf[(ev) * 256 + (idx)] = clock64(); } while (0)
-#else
-#define OG_TRACE_EVT(ev, idx) do { } while (0)
-#endif
 namespace tcl2 {
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;                 // smem ring (A raw + B hi + B lo); the TMEM A ring has the same depth

@@ -6,6 +6,13 @@
 #include <cuda.h>
 
 namespace og {
+#ifdef OG_TRACE
+// debug build only (scripts/trace_*.py): event timestamps of CTA 0
+__device__ long long og_trace_buf[8 * 256];
+#define OG_TRACE_EVT(ev, idx) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 256) og_trace_buf[(ev) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define OG_TRACE_EVT(ev, idx) do { } while (0)
+#endif
 namespace tc {
 
 // ----------------------------------------------------------------------------- addresses
