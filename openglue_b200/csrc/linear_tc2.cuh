@@ -3,22 +3,24 @@
 //
 // Why chunked: the tensor core adds into its TMEM accumulator with truncation (measured: error grows
 // ~linearly with the number of accumulation steps, 4e-6 relative at K=512, 10x worse than fp32 FMA).
-// Here the accumulator only ever holds K=64 worth of products (24 MMAs); a second warpgroup drains it
+// Here the accumulator only ever holds K=64 worth of products (24 MMAs); the epilogue warpgroups drain it
 // into registers with round-to-nearest adds while the tensor pipe fills the other accumulator buffer.
 // That restores fp32-GEMM accuracy (3-6e-7 relative) at no cost in tensor throughput.
 //
-// Data movement: one TMA producer thread streams, per 32-wide K block, the raw fp32 A tile (128 x 32)
-// and the pre-split B_hi / B_lo tiles (128 x 32 each) into a 4-deep 128B-swizzled smem ring.  The four
-// converter warps read their A row from smem (conflict-free through the swizzle), split it hi/lo in
-// registers and tcgen05.st it into a 4-deep TMEM ring, so A never occupies MMA-side smem bandwidth.
+// Data movement: one TMA producer thread streams, per 32-wide K block, the raw fp32 A tile (128 x 32) and
+// the pre-split B_hi / B_lo tiles into a 128B-swizzled smem ring.  Four converter warps read their A row
+// from smem (conflict-free through the swizzle), split it hi/lo in registers and tcgen05.st it into a TMEM
+// ring, so A never occupies MMA-side smem bandwidth.  Row-major outputs leave through swizzled smem staging
+// tiles and TMA stores.
 // 16 warps: WG0 / WG1 = accumulate + epilogue for output columns [0,64) / [64,128) (64 fp32 accumulators per
 // thread, so 128 registers per thread suffice for every role), WG2 = A converters, warp 12 = TMA producer,
-// warp 13 = MMA issue + TMEM alloc.
-// One CTA per SM, static round-robin tile schedule (n fastest, so CTAs that run together share A in L2).
-// Thread-block clusters of CL CTAs along M share the B tile: every CTA TMA-loads 1/CL of its rows with
-// .multicast::cluster into all CL shared memories, cutting B's L2->SM traffic by CL (measured before: the
-// kernel moved 6-7.5 TB/s out of L2, i.e. it was L2-bound with B = 2/3 of the bytes).  Stage recycling across
-// CTAs: a producer tells its peers when its own stage is free and issues only when all peers said the same.
+// warp 13 = MMA issue + TMEM alloc.  One CTA per SM, static round-robin tile schedule (n fastest).
+//
+// PAIR = 1 (cta_group::2): two CTAs of a cluster work on 256 rows x 128 columns.  Each stages only HALF of the
+// B tile (64 of its 128 rows); the leader CTA issues M = 256 MMAs that read B from both shared memories and A /
+// D from both tensor memories.  Per CTA and K block this removes 16 KB of TMA writes and 24 KB of MMA operand
+// reads from shared memory - the resource the single-CTA form is bound by (event trace: 128 KB of smem traffic
+// per K block = 1000 cycles at 128 B/clk against 768 cycles of MMA work).
 #pragma once
 #include "tc_common.cuh"
 #include "linear_tc.cuh"     // TcLinearArgs
@@ -28,28 +30,35 @@
 namespace og {
 namespace tcl2 {
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;                 // smem ring (A raw + B hi + B lo); the TMEM A ring has the same depth
 constexpr int CHUNK_KB = 2;               // K blocks per accumulator chunk (K = 64)
-constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KB
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;
+constexpr int TILE_BYTES = 128 * BK * 4;  // 16 KB: a [128 x 32] fp32 tile
 constexpr int THREADS = 512;
-constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32), s < STAGES
+constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ring 256 + 64 s (hi 32 | lo 32)
 constexpr int COL_A = 256;
+constexpr int OUT_TILE = 128 * 32 * 4;    // one staged [128 rows x 32 cols] output chunk (16 KB)
+constexpr int OUT_BYTES = 2 * 2 * OUT_TILE;  // 2 epilogue warpgroups x 2 buffers
+constexpr int MAX_STAGES = 4;
+
+template <int PAIR> struct Cfg {
+  static constexpr int STAGES = PAIR ? 4 : 3;                 // smem ring depth = TMEM A ring depth
+  static constexpr int BROWS = BN / (PAIR ? 2 : 1);           // rows of B staged by one CTA
+  static constexpr int B_TILE = BROWS * BK * 4;               // bytes of its B_hi (or B_lo) part
+  static constexpr int STAGE_BYTES = TILE_BYTES + 2 * B_TILE; // A raw | B_hi | B_lo
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + 2048;
+};
 
 struct __align__(16) Barriers {
-  uint64_t full[STAGES], empty[STAGES], a_full[STAGES], a_empty[STAGES], acc_full[2], acc_empty[2], peer_free[STAGES];
+  uint64_t a_land[MAX_STAGES], b_full[MAX_STAGES], empty[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
+  uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
   alignas(16) float rscale[BN];
 };
-constexpr int OUT_TILE = 128 * 32 * 4;    // one staged [128 rows x 32 cols] output chunk (16 KB)
-constexpr int OUT_BYTES = 2 * 2 * OUT_TILE;  // 2 epilogue warpgroups x 2 buffers
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + 2048;
 
-struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of CL m-tiles; ngroups = ntn * ntmg * batch
+struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of (PAIR ? 2 : 1) m-tiles; ngroups = ntn * ntmg * batch
 }  // namespace tcl2
 
-template <int CL>
+template <int PAIR>
 __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
@@ -60,37 +69,46 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
                                                                       TcLinearArgs a, tcl2::Sched sc, int y_tma) {
   using namespace tcl2;
   using namespace tc;
+  using C = Cfg<PAIR>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE = C::B_TILE, NC = PAIR ? 2 : 1;
   extern __shared__ uint8_t og_tcl2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl2_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;                          // [2 warpgroups][2 buffers][16 KB]
   Barriers* bars = reinterpret_cast<Barriers*>(s_out + OUT_BYTES);
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction (setmaxnreg needs it)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-  const int g_first = blockIdx.x / CL, g_stride = gridDim.x / CL;     // cluster index / number of clusters
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;                // 0 = leader of the pair
+  const int g_first = blockIdx.x / NC, g_stride = gridDim.x / NC;      // pair (or CTA) index / count
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 129);       // 128 converter threads + MMA commit
-      mbar_init(&bars->a_full[i], 128); mbar_init(&bars->a_empty[i], 1);
-      mbar_init(&bars->peer_free[i], CL > 1 ? CL - 1 : 1);
+      mbar_init(&bars->a_land[i], 1); mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->empty[i], 4 + 1);                     // 4 converter warps + the MMA commit
+      mbar_init(&bars->a_full[i], 4 * NC); mbar_init(&bars->a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8 * NC); }
     fence_barrier_init();
     prefetch_tensormap(&map_a); prefetch_tensormap(&map_a2);
     prefetch_tensormap(&map_bhi); prefetch_tensormap(&map_blo);
   }
-  if (warp == 13) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (PAIR) cluster_sync_all();                              // the peer's barriers exist before anyone signals them
+  if (warp == 13) { if (PAIR) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base); else tmem_alloc<TMEM_COLS>(&bars->tmem_base); }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();                            // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  // one arrival per warp (after every lane has completed and fenced its own TMEM / smem accesses) on a barrier that
+  // lives in the leader CTA
+  auto arrive_leader = [&](uint64_t* bar) {
+    __syncwarp();
+    if (lane == 0) { if (!PAIR || crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); }
+  };
+  auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
 
-  // group tile t = CL consecutive m-tiles x one n-tile; this CTA takes m-tile number `crank` of the group
+  // group tile t = NC consecutive m-tiles x one n-tile; this CTA takes m-tile number `crank` of the group
   auto tile_coords = [&](int t, int& m0, int& n0, int& bz) {
     n0 = (t % sc.ntn) * BN;
-    m0 = (((t / sc.ntn) % sc.ntmg) * CL + (int)crank) * BM;
+    m0 = (((t / sc.ntn) % sc.ntmg) * NC + (int)crank) * BM;
     bz = t / (sc.ntn * sc.ntmg);
   };
 
@@ -102,35 +120,30 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
       for (int t = g_first; t < sc.ngroups; t += g_stride) {
         int m0, n0, bz; tile_coords(t, m0, n0, bz);
         const int arow = bz * a.rows + m0;                     // batches are dense: row index into [batch*rows, K]
-        const int brow = n0 + bz * a.b_rows_per_batch;
+        const int brow = n0 + bz * a.b_rows_per_batch + (int)crank * C::BROWS;     // my part of the B tile's rows
         for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&bars->empty[s], ph ^ 1);                  // my consumers released stage s
+          mbar_wait(&bars->empty[s], ph ^ 1);                  // my converters and the MMAs released stage s
           OG_TRACE_EVT(0, it);
-          if (CL > 1) {
-#pragma unroll
-            for (uint32_t r = 0; r < (uint32_t)CL; ++r) if (r != crank) mbar_arrive_remote(&bars->peer_free[s], r);
-            mbar_wait(&bars->peer_free[s], ph);                // ... and so did every peer's (they will receive my B slice)
-          }
-          mbar_arrive_expect_tx(&bars->full[s], STAGE_BYTES);
           uint8_t* dst = smem + s * STAGE_BYTES;
           const int k = kb * BK;
-          if (k < a.k1) tma_load_2d(dst, &map_a, &bars->full[s], k, arow);
-          else          tma_load_2d(dst, &map_a2, &bars->full[s], k - a.k1, arow);
-          if (CL > 1) {                                        // my 128/CL rows of B_hi / B_lo go to every CTA of the cluster
-            constexpr int SL = BN / CL;
-            tma_load_2d_mcast(dst + TILE_BYTES + crank * SL * 128, &map_bhi, &bars->full[s], k, brow + crank * SL, (uint16_t)((1u << CL) - 1));
-            tma_load_2d_mcast(dst + 2 * TILE_BYTES + crank * SL * 128, &map_blo, &bars->full[s], k, brow + crank * SL, (uint16_t)((1u << CL) - 1));
+          mbar_arrive_expect_tx(&bars->a_land[s], TILE_BYTES);
+          if (k < a.k1) tma_load_2d(dst, &map_a, &bars->a_land[s], k, arow);
+          else          tma_load_2d(dst, &map_a2, &bars->a_land[s], k - a.k1, arow);
+          if (crank == 0) mbar_arrive_expect_tx(&bars->b_full[s], NC * 2 * B_TILE);   // both CTAs' B parts report to the leader
+          if (PAIR) {
+            tma_load_2d_pair(dst + TILE_BYTES, &map_bhi, &bars->b_full[s], k, brow);
+            tma_load_2d_pair(dst + TILE_BYTES + B_TILE, &map_blo, &bars->b_full[s], k, brow);
           } else {
-            tma_load_2d(dst + TILE_BYTES, &map_bhi, &bars->full[s], k, brow);
-            tma_load_2d(dst + 2 * TILE_BYTES, &map_blo, &bars->full[s], k, brow);
+            tma_load_2d(dst + TILE_BYTES, &map_bhi, &bars->b_full[s], k, brow);
+            tma_load_2d(dst + TILE_BYTES + B_TILE, &map_blo, &bars->b_full[s], k, brow);
           }
         }
       }
     }
-  } else if (warp == 13) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_tf32(BM, BN);
+  } else if (warp == 13 && crank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only when paired)
+    const uint32_t idesc = make_idesc_tf32(BM * NC, BN);
     int it = 0, g = 0;                                         // k-block and chunk counters
     for (int t = g_first; t < sc.ngroups; t += g_stride) {
       for (int c = 0; c < sc.nchunks; ++c, ++g) {
@@ -140,25 +153,32 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         const int kb_end = min((c + 1) * CHUNK_KB, sc.nkb);
         for (int kb = c * CHUNK_KB; kb < kb_end; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&bars->full[s], ph);                       // B tiles landed
+          mbar_wait(&bars->b_full[s], ph);                     // B tiles landed (in both CTAs)
           OG_TRACE_EVT(3, it);
-          mbar_wait(&bars->a_full[s], ph);                     // A split written to TMEM
+          mbar_wait(&bars->a_full[s], ph);                     // A split written to TMEM (in both CTAs)
           tc_fence_after();
           OG_TRACE_EVT(4, it);
           if (elect_one()) {
-            const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + TILE_BYTES), blo = bhi + TILE_BYTES;
+            const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + TILE_BYTES), blo = bhi + B_TILE;
             const uint32_t d = tmem + buf * 128;
 #pragma unroll
             for (int kk = 0; kk < BK / 8; ++kk) {
               const uint64_t dbhi = make_sdesc_sw128(bhi + kk * 32), dblo = make_sdesc_sw128(blo + kk * 32);
               const uint32_t ahi = tmem + COL_A + s * 64 + kk * 8, alo = ahi + 32;
-              umma_tf32_ts(d, alo, dbhi, idesc, (kb > c * CHUNK_KB || kk) ? 1u : 0u);
-              umma_tf32_ts(d, ahi, dblo, idesc, 1u);
-              umma_tf32_ts(d, ahi, dbhi, idesc, 1u);
+              const uint32_t acc0 = (kb > c * CHUNK_KB || kk) ? 1u : 0u;
+              if (PAIR) {
+                umma_tf32_ts_pair(d, alo, dbhi, idesc, acc0);
+                umma_tf32_ts_pair(d, ahi, dblo, idesc, 1u);
+                umma_tf32_ts_pair(d, ahi, dbhi, idesc, 1u);
+              } else {
+                umma_tf32_ts(d, alo, dbhi, idesc, acc0);
+                umma_tf32_ts(d, ahi, dblo, idesc, 1u);
+                umma_tf32_ts(d, ahi, dbhi, idesc, 1u);
+              }
             }
-            umma_commit(&bars->empty[s]);
-            umma_commit(&bars->a_empty[s]);
-            if (kb == kb_end - 1) umma_commit(&bars->acc_full[buf]);
+            commit(&bars->empty[s]);
+            commit(&bars->a_empty[s]);
+            if (kb == kb_end - 1) commit(&bars->acc_full[buf]);
           }
           __syncwarp();
         }
@@ -174,7 +194,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     for (int t = g_first; t < sc.ngroups; t += g_stride) {
       for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(&bars->full[s], ph);
+        mbar_wait(&bars->a_land[s], ph);
         if (warp == 8 && lane == 0) OG_TRACE_EVT(1, it);
         const uint8_t* arow = smem + s * STAGE_BYTES + trow * 128;
         uint32_t hi[32], lo[32];
@@ -184,7 +204,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
           split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
           split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
         }
-        mbar_arrive(&bars->empty[s]);                          // this thread is done with the smem A tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);           // this warp is done with the smem A tile
         mbar_wait(&bars->a_empty[s], ph ^ 1);
         tc_fence_after();
         const uint32_t taddr = tmem + lane_base + COL_A + s * 64;
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         tmem_st_32x32(taddr + 32, lo);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->a_full[s]);
+        arrive_leader(&bars->a_full[s]);
         if (warp == 8 && lane == 0) OG_TRACE_EVT(2, it);
       }
     }
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
           for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(v[j]);
         }
         tc_fence_before();
-        mbar_arrive(&bars->acc_empty[buf]);
+        arrive_leader(&bars->acc_empty[buf]);
         if (warp == 0 && lane == 0) OG_TRACE_EVT(6, g);
       }
       // ---- epilogue for this tile (overlaps the next tile's first chunks)
@@ -328,8 +349,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();                            // no CTA leaves while a peer may still write its smem / barriers
-  if (warp == 13) { tc_fence_after(); tmem_dealloc<tcl2::TMEM_COLS>(tmem); }
+  if (PAIR) cluster_sync_all();                              // no CTA leaves while the peer may still read its smem / signal its barriers
+  if (warp == 13) { tc_fence_after(); if (PAIR) tmem_dealloc_pair<tcl2::TMEM_COLS>(tmem); else tmem_dealloc<tcl2::TMEM_COLS>(tmem); }
 }
 
 inline bool linear_tc2_eligible(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb) {
@@ -339,10 +360,12 @@ inline bool linear_tc2_eligible(const TcLinearArgs& a, const float* Bhi, const f
   return true;
 }
 
-template <int CL>
-inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
-                                cudaStream_t stream) {
+template <int PAIR>
+inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
+                               cudaStream_t stream) {
   using namespace tcl2;
+  using C = Cfg<PAIR>;
+  constexpr int NC = PAIR ? 2 : 1;
   const int K = a.k1 + a.k2;
   CUtensorMap ma, ma2, mhi, mlo;
   int rc;
@@ -350,8 +373,8 @@ inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const f
   if ((rc = tc::make_tmap_2d(&ma, a.A, arows, (uint64_t)a.k1, (uint64_t)a.lda, BM)) != OG_OK) return rc;
   if (a.A2) { if ((rc = tc::make_tmap_2d(&ma2, a.A2, arows, (uint64_t)a.k2, (uint64_t)a.lda2, BM)) != OG_OK) return rc; }
   else ma2 = ma;
-  if ((rc = tc::make_tmap_2d(&mhi, Bhi, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
-  if ((rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN / CL)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mhi, Bhi, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, C::BROWS)) != OG_OK) return rc;
+  if ((rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, C::BROWS)) != OG_OK) return rc;
   // row-major outputs go out through TMA stores when their rows are 16-byte aligned
   CUtensorMap my = ma, myh = ma, myl = ma;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -363,50 +386,39 @@ inline int linear_tc2_launch_cl(const TcLinearArgs& a, const float* Bhi, const f
   }
   static bool attr_set = false;
   if (!attr_set) {
-    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   Sched sc;
-  sc.ntmg = cdiv(cdiv(a.rows, BM), CL); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
+  sc.ntmg = cdiv(cdiv(a.rows, BM), NC); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
   sc.nkb = cdiv(K, BK); sc.nchunks = cdiv(sc.nkb, CHUNK_KB);
   const int sms = device_info().ok ? device_info().sm_count : 148;
-  const int nclusters = std::min(sc.ngroups, sms / CL);
+  const int nclusters = std::min(sc.ngroups, sms / NC);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * CL);
+  cfg.gridDim = dim3(nclusters * NC);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<CL>, ma, ma2, mhi, mlo, my, myh, myl, a, sc, y_tma));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR>, ma, ma2, mhi, mlo, my, myh, myl, a, sc, y_tma));
   launch_counter()++;
   return OG_OK;
 }
 
-// Cluster size along M (B-tile multicast).  Measured on B200 (profiles/README.md): 2-CTA clusters are ~5% slower and
-// 4-CTA clusters 2.8x slower than no clusters - the kernel is bound by the depth of its smem ring (bytes in flight per
-// SM), which multicast does not change, and the cross-CTA stage handshake adds latency.  Default 1; OG_TC_CLUSTER=2|4
-// keeps the path testable.
-inline int linear_tc2_cluster_size() {
-  static int cl = [] {
-    const char* e = getenv("OG_TC_CLUSTER");
-    int v = e ? atoi(e) : 1;
-    return (v == 1 || v == 2 || v == 4) ? v : 1;
-  }();
-  return cl;
+// OG_GEMM_PAIR=0 selects the single-CTA form (cross-check of the cta_group::2 path)
+inline int linear_tc2_pair_mode() {
+  static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  return v;
 }
 
 inline int linear_tc2_launch(const TcLinearArgs& a, const float* Bhi, const float* Blo, int64_t ldb, int64_t b_total_rows,
                              cudaStream_t stream) {
-  int cl = linear_tc2_cluster_size();
-  while (cl > 1 && cdiv(a.rows, tcl2::BM) < cl) cl >>= 1;              // tiny problems: no point in phantom m-tiles
-  switch (cl) {
-    case 4: return linear_tc2_launch_cl<4>(a, Bhi, Blo, ldb, b_total_rows, stream);
-    case 2: return linear_tc2_launch_cl<2>(a, Bhi, Blo, ldb, b_total_rows, stream);
-    default: return linear_tc2_launch_cl<1>(a, Bhi, Blo, ldb, b_total_rows, stream);
-  }
+  const bool pair = linear_tc2_pair_mode() != 0 && cdiv(a.rows, tcl2::BM) >= 2;     // tiny problems: no phantom m-tiles
+  return pair ? linear_tc2_launch_t<1>(a, Bhi, Blo, ldb, b_total_rows, stream)
+              : linear_tc2_launch_t<0>(a, Bhi, Blo, ldb, b_total_rows, stream);
 }
 
 }  // namespace og
