@@ -49,7 +49,7 @@ template <int PAIR> struct Cfg {
 
 struct __align__(16) Barriers {
   uint64_t a_land[MAX_STAGES], b_full[MAX_STAGES], empty[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[2], acc_empty[2], r_full[2];     // r_full[h]: residual chunks of warpgroup h landed in its staging buffers
   uint32_t tmem_base;
   alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
   alignas(16) float rscale[BN];
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap map_y,
                                                                       const __grid_constant__ CUtensorMap map_yhi,
                                                                       const __grid_constant__ CUtensorMap map_ylo,
-                                                                      TcLinearArgs a, tcl2::Sched sc, int y_tma) {
+                                                                      const __grid_constant__ CUtensorMap map_r,
+                                                                      TcLinearArgs a, tcl2::Sched sc, int y_tma, int r_tma) {
   using namespace tcl2;
   using namespace tc;
   using C = Cfg<PAIR>;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
       mbar_init(&bars->empty[i], 4 + 1);                     // 4 converter warps + the MMA commit
       mbar_init(&bars->a_full[i], 4 * NC); mbar_init(&bars->a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8 * NC); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8 * NC); mbar_init(&bars->r_full[i], 1); }
     fence_barrier_init();
     prefetch_tensormap(&map_a); prefetch_tensormap(&map_a2);
     prefetch_tensormap(&map_bhi); prefetch_tensormap(&map_blo);
@@ -227,12 +228,20 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     const int wg_tid = threadIdx.x & 127;
     int nstore = 0;                                            // staged stores issued by this warpgroup so far
     const bool vec_r = a.R && (a.ldr % 4 == 0) && (a.strideR % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
-    int g = 0;
-    for (int t = g_first; t < sc.ngroups; t += g_stride) {
+    int g = 0, ntile = 0;
+    for (int t = g_first; t < sc.ngroups; t += g_stride, ++ntile) {
       int m0, n0, bz; tile_coords(t, m0, n0, bz);
       float racc[HN];
 #pragma unroll
       for (int j = 0; j < HN; ++j) racc[j] = 0.f;
+      if (r_tma && wg_tid == 0) {
+        // residual tile of this warpgroup's 64 columns -> its two staging buffers, in flight during the whole main loop
+        // (per-thread row loads of R cost what the per-thread row stores did: ~1/3 of the tile time on the fc.3 GEMM)
+        tma_store_wait_read<0>();                              // the previous tile's stores no longer read the buffers
+        mbar_arrive_expect_tx(&bars->r_full[half], 2 * OUT_TILE);
+        tma_load_3d(s_out + (half * 2 + 0) * OUT_TILE, &map_r, &bars->r_full[half], n0 + half * HN, m0, bz);
+        tma_load_3d(s_out + (half * 2 + 1) * OUT_TILE, &map_r, &bars->r_full[half], n0 + half * HN + 32, m0, bz);
+      }
       for (int c = 0; c < sc.nchunks; ++c, ++g) {
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_full[buf], gph);
@@ -279,7 +288,18 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
         }
-        if (Rrow && row_ok) {
+        if (r_tma) {                                           // residual chunk cc sits (swizzled) in staging buffer cc
+          if (cc == 0) mbar_wait(&bars->r_full[half], ntile & 1);
+          nstore = cc;                                         // ... and the result goes back out through the same buffer
+          const uint8_t* rsrc = s_out + (half * 2 + cc) * OUT_TILE + trow * 128;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 r = *reinterpret_cast<const float4*>(rsrc + ((c4 ^ (trow & 7)) * 16));
+            const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl + 4 * c4]);
+            y[4 * c4] = fmaf(sv.x, r.x, y[4 * c4]);         y[4 * c4 + 1] = fmaf(sv.y, r.y, y[4 * c4 + 1]);
+            y[4 * c4 + 2] = fmaf(sv.z, r.z, y[4 * c4 + 2]); y[4 * c4 + 3] = fmaf(sv.w, r.w, y[4 * c4 + 3]);
+          }
+        } else if (Rrow && row_ok) {
           if (cb + 31 < a.nout && vec_r) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         // ~16K cycles per tile.
         auto stage_store = [&](const CUtensorMap* map, const uint32_t (&v)[32]) {
           uint8_t* buf = s_out + (half * 2 + (nstore & 1)) * OUT_TILE;
-          if (wg_tid == 0) tma_store_wait_read<1>();           // the store that last read this buffer is done with it
+          if (wg_tid == 0 && !r_tma) tma_store_wait_read<1>(); // the store that last read this buffer is done with it
           asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
           uint8_t* dst = buf + trow * 128;
 #pragma unroll
@@ -384,6 +404,10 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
     if (a.Yhi && (rc = tc::make_tmap_3d(&myh, a.Yhi, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
     if (a.Yhi && (rc = tc::make_tmap_3d(&myl, a.Ylo, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
   }
+  // residual through TMA as well: needs the staging buffers for itself, so only without split outputs
+  CUtensorMap mr = ma;
+  const int r_tma = y_tma && a.R && a.Y && !a.Yhi && a.ldr % 4 == 0 && a.strideR % 4 == 0 && al16(a.R) && a.nout % 32 == 0;
+  if (r_tma && (rc = tc::make_tmap_3d(&mr, a.R, a.batch, a.rows, a.nout, a.ldr, a.strideR, BM)) != OG_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -403,14 +427,16 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR>, ma, ma2, mhi, mlo, my, myh, myl, a, sc, y_tma));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma, r_tma));
   launch_counter()++;
   return OG_OK;
 }
 
-// OG_GEMM_PAIR=0 selects the single-CTA form (cross-check of the cta_group::2 path)
+// OG_GEMM_PAIR=1 selects the cta_group::2 form.  Parity-clean, but measured SLOWER on B200 (137 vs 186 TF/s on the
+// QKV shape; event trace: ~1850 vs ~1400 cycles per K block): the M = 256 MMAs take about twice as long per
+// instruction, so the halved smem traffic buys nothing, and the cross-CTA barrier hops add latency.  Default 0.
 inline int linear_tc2_pair_mode() {
-  static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 0; }();
   return v;
 }
 

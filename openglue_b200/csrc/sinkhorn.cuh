@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <math_constants.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace og {
 
@@ -255,8 +256,12 @@ inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
   else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > 2048 columns not supported (swap the images)", m);
   const int sms = device_info().ok ? device_info().sm_count : 148;
   p->pairs_per_launch = B < sms ? B : sms;
+  // experiment knobs: OG_SINK_PAIRS = pairs per launch (L2 blocking), OG_SINK_SP = max strips per pair
+  static const int env_pairs = [] { const char* e = getenv("OG_SINK_PAIRS"); return e ? atoi(e) : 0; }();
+  static const int env_sp = [] { const char* e = getenv("OG_SINK_SP"); return e ? atoi(e) : 16; }();
+  if (env_pairs > 0 && env_pairs < p->pairs_per_launch) p->pairs_per_launch = env_pairs;
   int sp = sms / p->pairs_per_launch;
-  if (sp > 16) sp = 16;
+  if (sp > env_sp) sp = env_sp;
   const int max_sp = cdiv(n + 1, SINK_WARPS);
   if (sp > max_sp) sp = max_sp;
   if (sp < 1) sp = 1;
