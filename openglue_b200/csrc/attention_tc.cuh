@@ -2,7 +2,9 @@
 // Replaces softmax_attention (reference models/superglue/attention.py:8-19); the N x M probability
 // tensor never exists outside TMEM.
 //
-// One CTA = 128 queries of one (batch, head); key blocks of 64.
+// Persistent: one CTA per SM loops over tiles; a tile = 128 queries of one (batch, head); key blocks of 64.
+// (TMEM allocation, barrier set-up, pipeline fill and the output epilogue of one tile overlap the next tile's
+// loads and MMAs; as one-tile CTAs these cost ~17% of the kernel.)
 //   S_i  = Q . K_i^T      A = Q hi/lo resident in TMEM (split once), B = K_i hi/lo tiles (TMA, smem)
 //   P_i  = exp(S_i*scale - m_i)   by 128 softmax threads, one query row each (row max / sum are
 //                                 thread-local: no shuffles), written back to TMEM split hi/lo
@@ -21,6 +23,7 @@
 #include "tc_common.cuh"
 #include <math_constants.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace og {
 
@@ -29,6 +32,7 @@ struct TcAttnArgs {
   float* out; int64_t ldo, strideo;
   int batch, nq, nk, num_heads, d;
   float scale;
+  int nqg, ntiles;                              // query-block groups per sequence, total tiles (set by the launcher)
 };
 
 namespace tca {
@@ -42,7 +46,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct __align__(8) Barriers {
   uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  uint64_t q_ready, s_full[2], p_full[2], o_full[2], o_empty[2], all_done;
+  uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2];
   uint32_t tmem_base;
 };
 // CG = 1: one CTA per 128 queries.  CG = 2: a CTA pair (cta_group::2) per 256 queries; every MMA spans both SMs
@@ -50,7 +54,7 @@ struct __align__(8) Barriers {
 template <int DH, int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * DH * 4; }        // hi + lo
 template <int DH, int CG> __host__ __device__ constexpr int v_stage_bytes() { return 2 * (DH / CG) * BNK * 4; }
 template <int DH, int CG> __host__ __device__ constexpr int smem_bytes() {
-  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512 + 6 * 128 * 4;
+  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512 + 8 * 128 * 4;
 }
 }  // namespace tca
 
@@ -78,8 +82,14 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform (setmaxnreg)
   const int lane = threadIdx.x & 31;
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the pair
-  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (a.nk + BNK - 1) / BNK;
+  const int t_first = blockIdx.x / CG, t_stride = gridDim.x / CG;      // tile list of this CTA (pair)
+  // tile t -> (query-block group, head, batch); query groups fastest so that co-running CTAs share K / V in L2
+  auto tile_coords = [&](int t, int& q0, int& h, int& b) {
+    q0 = ((t % a.nqg) * CG + (int)crank) * BM;
+    h = (t / a.nqg) % a.num_heads;
+    b = t / (a.nqg * a.num_heads);
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -87,7 +97,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
     mbar_init(&bars->q_ready, 8 * CG);               // one arrival per softmax warp (8 per CTA); CG = 2: the leader also counts the peer's
-    mbar_init(&bars->all_done, 1);
+    mbar_init(&bars->q_free, 1);                     // every QK^T of the current tile has retired: Q may be replaced
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 8 * CG);
       mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG);
@@ -114,10 +124,13 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      int it = 0;                                   // key blocks loaded so far (ring position), across tiles
+      for (int t = t_first; t < a.ntiles; t += t_stride) {
+      int q0, h, b; tile_coords(t, q0, h, b);
       const int krow0 = b * a.nk;                   // K rows of this batch item
       const int vrow = b * a.d + h * DH;            // V^T rows (channels) of this (batch, head)
-      for (int i = 0; i < nblk; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
+      for (int i = 0; i < nblk; ++i, ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&bars->k_empty[s], ph ^ 1);
         if (crank == 0) mbar_arrive_expect_tx(&bars->k_full[s], CG * k_stage_bytes<DH, CG>());   // both CTAs' bytes land on the leader's barrier
         uint8_t* kd = sK + s * k_stage_bytes<DH, CG>();
@@ -147,6 +160,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
           }
         }
       }
+      }
     }
   } else if ((warp == 9 || warp == 10) && crank == 0) {
     // ------------------------------------------------------------------ MMA issuers (leader CTA only when paired)
@@ -159,8 +173,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       if (CG == 2) umma_tf32_ts_pair(d, at, bd, id, acc); else umma_tf32_ts(d, at, bd, id, acc);
     };
     if (warp == 9) {
-      mbar_wait(&bars->q_ready, 0);
-      for (int i = 0; i < nblk; ++i) {
+      int it = 0, nt = 0;                             // key blocks / tiles done so far
+      for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
+      mbar_wait(&bars->q_ready, nt & 1);              // this tile's Q is in TMEM
+      for (int iloc = 0; iloc < nblk; ++iloc, ++it) {
+        const int i = it;                             // global block index: ring / buffer parity run across tiles
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
         OG_TRACE_EVT(0, i);
         mbar_wait(&bars->k_full[s], ph);
@@ -180,11 +197,14 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
           }
           commit(&bars->k_empty[s]);
           commit(&bars->s_full[j]);
+          if (iloc == nblk - 1) commit(&bars->q_free);   // the tile's last QK^T: Q can be replaced once it retires
         }
         __syncwarp();
       }
+      }
     } else {
-      for (int i = 0; i < nblk; ++i) {
+      const int ntot = nblk * ((a.ntiles - t_first + t_stride - 1) / t_stride);   // all key blocks of all my tiles
+      for (int i = 0; i < ntot; ++i) {
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1, jph = (i >> 1) & 1;
         OG_TRACE_EVT(2, i);
         mbar_wait(&bars->v_full[s], ph);
@@ -207,7 +227,6 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
           }
           commit(&bars->v_empty[s]);
           commit(&bars->o_full[j]);
-          if (i == nblk - 1) commit(&bars->all_done);
         }
         __syncwarp();
       }
@@ -223,20 +242,34 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     const int g = warp >> 2;
     const int qd = warp & 3;
     const int trow = qd * 32 + lane;
-    const int grow = q0 + trow;
-    const bool row_ok = grow < a.nq;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float* xch = reinterpret_cast<float*>(bars + 1);                   // [2 parities][2 warpgroups][128] row maxima, then [2][128] sums
-
-    {   // my half of the Q row -> split -> TMEM (A operand of every QK^T)
+    const float c1 = a.scale * LOG2E;
+    int it = 0, nt = 0;                              // key blocks / tiles done so far (buffer parities run across tiles)
+    float4 qv[HD / 4];                               // this thread's half Q row of the NEXT tile to start
+    auto load_q = [&](int t) {
+      int q0, h, b; tile_coords(t, q0, h, b);
+      const int grow = q0 + trow;
       const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH + g * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c)
+        qv[c] = (grow < a.nq) ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (t_first < a.ntiles) load_q(t_first);
+
+#pragma unroll 1
+    for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
+    int q0, h, b; tile_coords(t, q0, h, b);
+    const int grow = q0 + trow;
+    const bool row_ok = grow < a.nq;
+    {   // my half of the Q row (prefetched during the previous tile) -> split -> TMEM (A operand of every QK^T of this tile)
+      if (nt >= 1) { mbar_wait(&bars->q_free, (nt - 1) & 1); tc_fence_after(); }   // previous tile's QK^Ts have all retired
       if constexpr (HD == 32) {
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
-          split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          split_tf32_fast(qv[c].x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(qv[c].y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(qv[c].z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(qv[c].w, hi[4 * c + 3], lo[4 * c + 3]);
         }
         tmem_st_32x32(tmem + lane_base + COL_QHI + g * HD, hi);
         tmem_st_32x32(tmem + lane_base + COL_QLO + g * HD, lo);
@@ -244,9 +277,8 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          split_tf32_fast(v.x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(v.y, hi[4 * c + 1], lo[4 * c + 1]);
-          split_tf32_fast(v.z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+          split_tf32_fast(qv[c].x, hi[4 * c + 0], lo[4 * c + 0]); split_tf32_fast(qv[c].y, hi[4 * c + 1], lo[4 * c + 1]);
+          split_tf32_fast(qv[c].z, hi[4 * c + 2], lo[4 * c + 2]); split_tf32_fast(qv[c].w, hi[4 * c + 3], lo[4 * c + 3]);
         }
         tmem_st_32x16(tmem + lane_base + COL_QHI + g * HD, hi);
         tmem_st_32x16(tmem + lane_base + COL_QLO + g * HD, lo);
@@ -262,10 +294,9 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     // Online softmax in the exp2 domain.  c1 = scale*log2(e); mc = fl(m*c1) is the running max in that domain and
     // is used consistently for p = 2^(s*c1 - mc) (one FFMA: the product is exact inside the fma, only the small
     // difference is rounded) and for the block-to-block correction 2^(mc_old - mc_new).
-    const float c1 = a.scale * LOG2E;
     float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, corr_prev = 0.f;
 
-    auto fold_o = [&](int i, float corr) {           // acc = acc * corr + my channels of O_i
+    auto fold_o = [&](int i, float corr) {           // acc = acc * corr + my channels of O_i   (i = global block index)
       const int j = i & 1, jph = (i >> 1) & 1;
       mbar_wait(&bars->o_full[j], jph);
       tc_fence_after();
@@ -289,10 +320,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     };
 
 #pragma unroll 1
-    for (int i = 0; i < nblk; ++i) {
+    for (int iloc = 0; iloc < nblk; ++iloc, ++it) {
+      const int i = it;                              // global block index
       const int j = i & 1, jph = (i >> 1) & 1;
       const uint32_t sp = tmem + lane_base + COL_SP + 128 * j + 32 * g;      // my 32 columns of S_i / P_hi
-      const int kbase = i * BNK + 32 * g;
+      const int kbase = iloc * BNK + 32 * g;
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
       if (warp == 0 && lane == 0) OG_TRACE_EVT(5, i); // softmax: S_i observed
@@ -331,13 +363,14 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       m_run = m_new; mc_run = mc;
       // P_i is on its way; now fold O_{i-1} (computed with m_{i-1}: its correction is the one saved last iteration).
       // Doing this AFTER the softmax keeps P_i off the critical path; O_{i-1}'s buffer is only needed again by PV_{i+1}.
-      if (i >= 1) fold_o(i - 1, corr_prev);
+      if (iloc >= 1) fold_o(i - 1, corr_prev);
       corr_prev = corr;
     }
-    fold_o(nblk - 1, corr_prev);
+    if (t + t_stride < a.ntiles) load_q(t + t_stride);   // next tile's Q row: in flight during this tile's last fold + epilogue
+    fold_o(it - 1, corr_prev);
 
-    // total row sum = sum of the two warpgroups' partial sums
-    float* xl = xch + 4 * 128;
+    // total row sum = sum of the two warpgroups' partial sums (buffer alternates per tile: one barrier suffices)
+    float* xl = xch + 4 * 128 + (nt & 1) * 256;
     xl[g * 128 + trow] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float inv = 1.f / (l_run + xl[(g ^ 1) * 128 + trow]);
@@ -346,6 +379,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
 #pragma unroll
       for (int c = 0; c < HD; c += 4)
         *reinterpret_cast<float4*>(orow + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+    }
     }
     tc_fence_before();
   }
@@ -370,8 +404,12 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
     OG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<DH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<DH, CG>()));
     attr_set = true;
   }
+  TcAttnArgs ap = a;
+  ap.nqg = cdiv(cdiv(a.nq, BM), CG);                                             // CG = 2: an odd last query block gets a phantom partner
+  ap.ntiles = ap.nqg * a.num_heads * a.batch;
+  const int sms = device_info().ok ? device_info().sm_count : 148;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(cdiv(a.nq, BM), CG) * CG, a.num_heads, a.batch);       // CG = 2: an odd last query block gets a phantom partner
+  cfg.gridDim = dim3(std::min(ap.ntiles, sms / CG) * CG);                        // persistent: one CTA (pair) per SM (pair)
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem_bytes<DH, CG>();
   cfg.stream = stream;
@@ -379,7 +417,7 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<DH, CG>, mkh, mkl, mvh, mvl, a));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<DH, CG>, mkh, mkl, mvh, mvl, ap));
   launch_counter()++;
   return OG_OK;
 }

@@ -58,7 +58,7 @@ struct __align__(16) Barriers {
 struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of (PAIR ? 2 : 1) m-tiles; ngroups = ntn * ntmg * batch
 }  // namespace tcl2
 
-template <int PAIR>
+template <int PAIR, int RTMA>
 __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap map_yhi,
                                                                       const __grid_constant__ CUtensorMap map_ylo,
                                                                       const __grid_constant__ CUtensorMap map_r,
-                                                                      TcLinearArgs a, tcl2::Sched sc, int y_tma, int r_tma) {
+                                                                      TcLinearArgs a, tcl2::Sched sc, int y_tma) {
+  constexpr bool r_tma = RTMA != 0;                          // residual tile arrives by TMA (separate instantiation: keeps the plain epilogue lean)
   using namespace tcl2;
   using namespace tc;
   using C = Cfg<PAIR>;
@@ -410,7 +411,8 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   if (r_tma && (rc = tc::make_tmap_3d(&mr, a.R, a.batch, a.rows, a.nout, a.ldr, a.strideR, BM)) != OG_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   Sched sc;
@@ -427,7 +429,8 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma, r_tma));
+  if (r_tma) { OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR, 1>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma)); }
+  else       { OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR, 0>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma)); }
   launch_counter()++;
   return OG_OK;
 }
