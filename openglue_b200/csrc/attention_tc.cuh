@@ -255,15 +255,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       for (int c = 0; c < HD / 4; ++c)
         qv[c] = (grow < a.nq) ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (t_first < a.ntiles) load_q(t_first);
-
-#pragma unroll 1
-    for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
-    int q0, h, b; tile_coords(t, q0, h, b);
-    const int grow = q0 + trow;
-    const bool row_ok = grow < a.nq;
-    {   // my half of the Q row (prefetched during the previous tile) -> split -> TMEM (A operand of every QK^T of this tile)
-      if (nt >= 1) { mbar_wait(&bars->q_free, (nt - 1) & 1); tc_fence_after(); }   // previous tile's QK^Ts have all retired
+    auto write_q = [&]() {                           // qv -> split -> TMEM (A operand of every QK^T of a tile)
       if constexpr (HD == 32) {
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -286,7 +278,16 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->q_ready);
-    }
+    };
+    if (t_first < a.ntiles) load_q(t_first);
+
+#pragma unroll 1
+    for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
+    int q0, h, b; tile_coords(t, q0, h, b);
+    const int grow = q0 + trow;
+    const bool row_ok = grow < a.nq;
+    if (nt == 0) write_q();                          // later tiles: written at the end of the previous tile (see below)
+    if (t + t_stride < a.ntiles) load_q(t + t_stride);   // next tile's Q row: in flight during this whole tile
 
     float acc[HD];
 #pragma unroll
@@ -366,7 +367,11 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       if (iloc >= 1) fold_o(i - 1, corr_prev);
       corr_prev = corr;
     }
-    if (t + t_stride < a.ntiles) load_q(t + t_stride);   // next tile's Q row: in flight during this tile's last fold + epilogue
+    if (t + t_stride < a.ntiles) {                   // hand the next tile's Q to the tensor pipe BEFORE this tile's last fold and
+      mbar_wait(&bars->q_free, nt & 1);              // epilogue: its first QK^T / softmax overlap them (all QK^T of this tile retired)
+      tc_fence_after();
+      write_q();
+    }
     fold_o(it - 1, corr_prev);
 
     // total row sum = sum of the two warpgroups' partial sums (buffer alternates per tile: one barrier suffices)
