@@ -227,6 +227,12 @@ int64_t og_workspace_bytes(const og_config* cfg, int batch, int n, int m) {
 
 int og_last_forward_launches(void) { return launch_counter(); }
 
+int og_set_tuning(int gemm_pair, int attention_pair) {
+  if (gemm_pair >= 0) linear_tc2_pair_mode() = gemm_pair ? 1 : 0;
+  if (attention_pair >= 0) attention_tc_pair_mode() = attention_pair ? 1 : 0;
+  return OG_OK;
+}
+
 int og_linear_fwd(const og_linear_args* a, int precision, void* stream) {
   OG_CHECK_ARG(a && a->A && a->W && (a->Y || a->Yt), "linear: null pointer");
   OG_CHECK_ARG(precision == OG_PREC_FP32, "linear: the tensor-core form takes pre-split weights (og_linear_tc_fwd)");

@@ -430,7 +430,7 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
 // OG_ATTN_PAIR=1 selects the cta_group::2 (CTA pair, M = 256) form.  It is parity-clean but measured ~15% slower than the
 // single-CTA form on B200 (profiles/README.md): the extra cross-CTA barrier hops per key block cost more than the halved
 // B-operand traffic and MMA count per SM give back.  Default 0.
-inline int attention_tc_pair_mode() {
+inline int& attention_tc_pair_mode() {
   static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 0; }();
   return v;
 }

@@ -438,7 +438,7 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
 // OG_GEMM_PAIR=1 selects the cta_group::2 form.  Parity-clean, but measured SLOWER on B200 (137 vs 186 TF/s on the
 // QKV shape; event trace: ~1850 vs ~1400 cycles per K block): the M = 256 MMAs take about twice as long per
 // instruction, so the halved smem traffic buys nothing, and the cross-CTA barrier hops add latency.  Default 0.
-inline int linear_tc2_pair_mode() {
+inline int& linear_tc2_pair_mode() {
   static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 0; }();
   return v;
 }

@@ -86,6 +86,23 @@ def test_attention_tc_operator(B, H, dh, nq, nk):
     assert (out.cpu().double() - ref).abs().max() <= 1e-5 * ref.abs().max()
 
 
+@pytest.fixture
+def paired_kernels():
+    """Run a test with the cta_group::2 (CTA pair) forms of the GEMM and attention kernels."""
+    _cabi.check(_cabi.lib().og_set_tuning(1, 1), 'og_set_tuning')
+    yield
+    _cabi.check(_cabi.lib().og_set_tuning(0, 0), 'og_set_tuning')
+
+
+def test_paired_kernel_forms_match_reference(golden, paired_kernels):
+    for name in ('small_planted', 'C1_planted'):
+        test_forward_tf32x3_matches_reference(golden, name)
+    test_attention_tc_operator(2, 4, 64, 200, 333)
+    test_attention_tc_operator(1, 4, 32, 129, 64)
+    test_linear_tc_operator(2, 1000, 256, 256, 392, 1, False)
+    test_linear_tc_operator(2, 300, 512, 0, 256, 2, False)
+
+
 @pytest.mark.parametrize('name', ['tiny_planted', 'small_planted', 'C1_planted', 'C1_flat'])
 def test_forward_tf32x3_matches_reference(golden, name):
     fx = golden(name)
