@@ -86,17 +86,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` and completes the
-// mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                                  uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-
 // TMA store: a 128B-swizzled smem tile -> global (3-D map [batch, rows, cols]: clips at the batch boundary)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -242,12 +231,6 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-
-// ----------------------------------------------------------------------------- register budget per warpgroup
-// One CTA = 3 warpgroups of 4 warps; the register file is partitioned per SM sub-partition, so each
-// warpgroup contributes one warp per partition.  Data-movement warpgroups hand registers to the math one.
-template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ----------------------------------------------------------------------------- tf32 split
 // x = hi + lo (+ <= 2^-23 |x|):  hi = rna_tf32(x), lo = rna_tf32(x - hi).  Both are tf32-exact, so the
