@@ -171,7 +171,8 @@ def bench_config(args, wl, per_gpu_batch):
             'pairs_per_gpu': per_gpu_batch, 'global_pairs': per_gpu_batch * args.gpus,
             'N': wl['n'], 'M': wl['m'], 'd': c['descriptor_dim'], 'stages': c['num_stages'],
             'sinkhorn_iters': c['num_iters'], 'parallelism': f'pairs sharded over {args.gpus} GPU(s), no data-path collective',
-            'l2': 'working set per step (scores 16.8 MB/pair + activations) exceeds the 126 MB L2; no explicit flush'}
+            'l2': 'working set per step (scores 16.8 MB/pair + activations) exceeds the 126 MB L2; no explicit flush',
+            'cuda_graph': bool(getattr(args, 'cuda_graph', 0))}
 
 
 def main():
@@ -184,6 +185,7 @@ def main():
     ap.add_argument('--pairs-per-gpu', type=int, default=None)
     ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'tf32x3'), choices=['fp32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cuda-graph', type=int, default=1, help='replay the launch schedule from a CUDA graph (default on)')
     args = ap.parse_args()
     wl = dict(BASELINE_CONFIGS[args.workload])
     if args.impl == 'reference':
@@ -218,7 +220,7 @@ def main():
     model = SuperGlue(cfg).eval()
     model.load_state_dict(synthetic_state_dict(cfg, seed=0))
     model = model.to(dev)
-    core = MatchingCore(model, MATCH_THRESHOLD, device=dev)
+    core = MatchingCore(model, MATCH_THRESHOLD, device=dev, use_cuda_graph=bool(args.cuda_graph))
     host = synthetic_pairs(batch, n, m, d, s_dim, family='planted', seed=1234 + rank)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}

@@ -151,6 +151,29 @@ def test_host_buffers_roundtrip(golden):
     assert torch.equal(res['matches0'], fx['matches0'])
 
 
+def test_cuda_graph_replay_matches_eager(golden):
+    """MatchingCore(use_cuda_graph=True): same answers as eager launches, across replays and new inputs."""
+    fx = golden('small_planted')
+    model = _model(fx['config'], fx['state_dict'], 'tf32x3')
+    eager = MatchingCore(model, fx['match_threshold'])
+    graphed = MatchingCore(model, fx['match_threshold'], use_cuda_graph=True)
+    data = _to_dev(fx['data'])
+    ref = eager(data, want_scores=True)
+    for _ in range(3):
+        got = graphed(data, want_scores=True)
+        assert torch.equal(got['matches0'], ref['matches0']) and torch.equal(got['scores'], ref['scores'])
+    data2 = dict(data)
+    data2['keypoints0'] = data['keypoints0'].flip(1).contiguous()            # same shapes, different values
+    data2['local_descriptors0'] = data['local_descriptors0'].flip(1).contiguous()
+    data2['side_info0'] = data['side_info0'].flip(1).contiguous()
+    ref2 = eager(data2, want_scores=True)
+    got2 = graphed(data2, want_scores=True)
+    assert torch.equal(got2['matches0'], ref2['matches0']) and torch.equal(got2['scores'], ref2['scores'])
+    host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in data2.items()}
+    got3 = graphed(host)
+    assert got3['matches0'].device.type == 'cpu' and torch.equal(got3['matches0'], ref2['matches0'].cpu())
+
+
 # --------------------------------------------------------------------------- operators
 @pytest.mark.parametrize('rows,k1,k2,nout,relu,resid,batch', [
     (200, 3, 0, 32, True, False, 1), (513, 256, 256, 512, True, False, 1), (130, 512, 0, 256, False, True, 1),
