@@ -4,6 +4,6 @@ Public surface mirrors the reference for this one path:
     SuperGlue(config).forward(data)  -> {'context_descriptors0', 'context_descriptors1', 'scores'}
     MatchingCore(superglue)(data)    -> {'matches0', 'matching_scores0', 'matches1', 'matching_scores1'}
 """
-from .superglue import MatchingCore, SuperGlue  # noqa: F401
+from .superglue import MatchingCore, PendingMatches, SuperGlue  # noqa: F401
 
 __version__ = '0.1.0'

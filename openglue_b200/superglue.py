@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _cabi
 from .packing import pack_weights
 
-__all__ = ['SuperGlue', 'MatchingCore']
+__all__ = ['SuperGlue', 'MatchingCore', 'PendingMatches']
 
 
 def _feed_forward_params(*sizes: int) -> nn.Sequential:
@@ -214,6 +214,17 @@ class SuperGlue(nn.Module):
         return self.run(data, want_matches=False)
 
 
+class PendingMatches:
+    """Result of :meth:`MatchingCore.submit`: host tensors that become valid at :meth:`wait`."""
+
+    def __init__(self, result: Dict[str, torch.Tensor], done: torch.cuda.Event):
+        self._result, self._done = result, done
+
+    def wait(self) -> Dict[str, torch.Tensor]:
+        self._done.synchronize()
+        return self._result
+
+
 class MatchingCore(nn.Module):
     """``SuperGlue`` + mutual-argmax match extraction: what ``MatchingTrainingModule.forward``
     (reference models/matching_module.py:149-187) computes from prepared features, fused into the
@@ -283,3 +294,61 @@ class MatchingCore(nn.Module):
             res = {k: v.to('cpu', non_blocking=True) for k, v in res.items()}
             torch.cuda.current_stream(dev).synchronize()
         return res
+
+    # ------------------------------------------------------------------ pipelined host API
+    def submit(self, data: dict) -> PendingMatches:
+        """Asynchronous form of ``forward`` for HOST batches (serving loop).  The H2D copy of this batch runs on an
+        upload stream into one of two device input-buffer sets while the previous batch is still computing; the
+        kernels run on the current (compute) stream; the D2H copy of the matches runs on a download stream behind
+        them.  ``submit`` returns at once; ``.wait()`` yields the dict ``forward`` returns for host input.  Keep at
+        most two batches in flight: the result buffers of a slot are reused by the second-next ``submit``."""
+        if data['keypoints0'].device.type != 'cpu':
+            raise ValueError('submit() takes host (CPU, ideally pinned) tensors; use forward() for device tensors')
+        dev = self.device or torch.device('cuda', torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            if not hasattr(self, '_pipe'):
+                self._pipe = {'h2d': torch.cuda.Stream(dev), 'd2h': torch.cuda.Stream(dev), 'slot': 0,
+                              'bufs': [None, None], 'free': [None, None], 'out': [None, None]}
+            pipe = self._pipe
+            slot = pipe['slot']
+            pipe['slot'] ^= 1
+            compute = torch.cuda.current_stream(dev)
+            shapes = tuple(tuple(data[k].shape) for k in self._TENSOR_KEYS)
+            if pipe['bufs'][slot] is None or pipe['bufs'][slot][0] != shapes:
+                pipe['bufs'][slot] = (shapes, {k: torch.empty(data[k].shape, dtype=torch.float32, device=dev)
+                                               for k in self._TENSOR_KEYS})
+                pipe['out'][slot] = None
+                # fresh blocks may be recycled from tensors the compute stream is still using (the allocator only
+                # orders reuse within one stream): the upload stream must not write them before that work is done
+                pipe['h2d'].wait_stream(compute)
+            bufs = pipe['bufs'][slot][1]
+            with torch.cuda.stream(pipe['h2d']):
+                if pipe['free'][slot] is not None:
+                    pipe['h2d'].wait_event(pipe['free'][slot])       # the kernels that last read this buffer set are done
+                for k in self._TENSOR_KEYS:
+                    bufs[k].copy_(data[k], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(pipe['h2d'])
+            compute.wait_event(landed)
+            dev_data = dict(data)
+            dev_data.update(bufs)
+            if self.use_cuda_graph:
+                out = self._run_graph(dev_data, dev)
+            else:
+                out = self.superglue.run(dev_data, want_matches=True, want_context=False)
+            computed = torch.cuda.Event()
+            computed.record(compute)
+            pipe['free'][slot] = computed
+            if pipe['out'][slot] is None:
+                pipe['out'][slot] = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in self._OUT_KEYS}
+            host_out = pipe['out'][slot]
+            with torch.cuda.stream(pipe['d2h']):
+                pipe['d2h'].wait_event(computed)
+                for k in self._OUT_KEYS:
+                    host_out[k].copy_(out[k], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(pipe['d2h'])
+            # the device-side results (graph-static, or allocator blocks of the compute stream) may be overwritten by
+            # later kernels only once they have been read back: a 0.4 MB copy, so this costs the pipeline nothing
+            compute.wait_event(done)
+        return PendingMatches(host_out, done)

@@ -122,6 +122,7 @@ def test_forward_matches_reference_c1(golden, name):
     (1, 300, 513, dict(descriptor_dim=128, num_stages=2, num_iters=40, side_info_size=6), 'planted'),
     (2, 256, 1100, dict(descriptor_dim=64, num_stages=1, num_iters=15, reg=0.5, use_offset=True,
                         residual=False), 'flat'),                                     # V=16 path, reg != 1
+    (1, 4096, 1024, dict(descriptor_dim=128, num_stages=1, num_iters=50, side_info_size=6), 'planted'),   # configs[4] shape
 ])
 @pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 def test_forward_matches_oracle(batch, n, m, kw, family, precision):
@@ -172,6 +173,37 @@ def test_cuda_graph_replay_matches_eager(golden):
     host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in data2.items()}
     got3 = graphed(host)
     assert got3['matches0'].device.type == 'cpu' and torch.equal(got3['matches0'], ref2['matches0'].cpu())
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_submit_pipeline_matches_blocking_forward(golden, graph):
+    """MatchingCore.submit()/wait() with two batches in flight: every batch gets the answer the blocking call gives."""
+    fx = golden('small_planted')
+    model = _model(fx['config'], fx['state_dict'], 'tf32x3')
+    blocking = MatchingCore(model, fx['match_threshold'], device=DEV)
+    piped = MatchingCore(model, fx['match_threshold'], device=DEV, use_cuda_graph=graph)
+    batches = []
+    for i in range(5):
+        h = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in fx['data'].items()}
+        if i % 2:
+            for k in ('keypoints0', 'local_descriptors0', 'side_info0'):
+                h[k] = h[k].flip(1).contiguous()
+        if i >= 3:
+            h['local_descriptors1'] = torch.nn.functional.normalize(h['local_descriptors1'] + 0.05 * i, dim=-1)
+        batches.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in h.items()})
+    want = [{k: v.clone() for k, v in blocking(h).items()} for h in batches]
+    got, pend = [], None
+    for h in batches:
+        nxt = piped.submit(h)
+        if pend is not None:
+            got.append({k: v.clone() for k, v in pend.wait().items()})
+        pend = nxt
+    got.append({k: v.clone() for k, v in pend.wait().items()})
+    for w, g in zip(want, got):
+        for k in ('matches0', 'matches1', 'matching_scores0', 'matching_scores1'):
+            assert g[k].device.type == 'cpu' and torch.equal(w[k], g[k]), k
+    with pytest.raises(ValueError):
+        piped.submit(_to_dev(fx['data']))
 
 
 # --------------------------------------------------------------------------- operators
