@@ -122,9 +122,9 @@ int og_superglue_forward(const og_config* cfg, const float* packed_weights,
 int og_last_forward_launches(void);
 
 /* Kernel-variant switches of the tcgen05 path (process-wide; -1 leaves a switch unchanged).
- *   gemm_pair / attention_pair = 1: cta_group::2 form (one MMA spans a CTA pair, M = 256); 0 (default): one CTA per tile.
- * Both forms are parity-tested; on B200 the paired forms measured slower (profiles/README.md).  Env defaults:
- * OG_GEMM_PAIR, OG_ATTN_PAIR.                                                                             */
+ *   gemm_pair / attention_pair = 1 (default): cta_group::2 form (one MMA spans a CTA pair, M = 256); 0: one CTA per tile.
+ * Both forms are parity-tested; on B200 the paired forms are ~7 % faster end to end (profiles/README.md).  Env
+ * defaults: OG_GEMM_PAIR, OG_ATTN_PAIR; a negative argument leaves that setting unchanged.                                                                           */
 int og_set_tuning(int gemm_pair, int attention_pair);
 
 /* ---------------------------------------------------------------------------------------------

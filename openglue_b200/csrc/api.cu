@@ -259,7 +259,7 @@ int og_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* strea
 
 #ifdef OG_TRACE
 int og_trace_read(long long* host_out) {     // debug build only
-  OG_CUDA(cudaMemcpyFromSymbol(host_out, og_trace_buf, sizeof(long long) * 8 * 256));
+  OG_CUDA(cudaMemcpyFromSymbol(host_out, og_trace_buf, sizeof(long long) * 2 * 16 * 256));
   return OG_OK;
 }
 #endif

@@ -427,11 +427,11 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
   return OG_OK;
 }
 
-// OG_ATTN_PAIR=1 selects the cta_group::2 (CTA pair, M = 256) form.  It is parity-clean but measured ~15% slower than the
-// single-CTA form on B200 (profiles/README.md): the extra cross-CTA barrier hops per key block cost more than the halved
-// B-operand traffic and MMA count per SM give back.  Default 0.
+// The cta_group::2 (CTA pair, M = 256) form is the default: each SM stages and reads only half of every K / V^T tile, which
+// takes the kernel off the shared-memory-bandwidth limit of the single-CTA form (0.563 -> 0.538 ms per self layer at the
+// headline shape).  OG_ATTN_PAIR=0 / og_set_tuning select the single-CTA form; both are parity-tested.
 inline int& attention_tc_pair_mode() {
-  static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char* e = getenv("OG_ATTN_PAIR"); return e ? atoi(e) : 1; }();
   return v;
 }
 

@@ -51,14 +51,18 @@ struct __align__(16) Barriers {
   uint64_t a_land[MAX_STAGES], b_full[MAX_STAGES], empty[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
   uint64_t acc_full[2], acc_empty[2], r_full[2];     // r_full[h]: residual chunks of warpgroup h landed in its staging buffers
   uint32_t tmem_base;
-  alignas(16) float bias[BN];           // per-tile epilogue vectors staged by the epilogue warps (read as float4)
-  alignas(16) float rscale[BN];
+  alignas(16) float bias[2][BN];        // per-tile epilogue vectors (tile parity), staged by each epilogue warpgroup for its
+  alignas(16) float rscale[2][BN];      // own 64 columns at tile start, while it waits for the first accumulator chunk
 };
 
 struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };   // ntmg: groups of (PAIR ? 2 : 1) m-tiles; ngroups = ntn * ntmg * batch
 }  // namespace tcl2
 
-template <int PAIR, int RTMA>
+// OUTK prunes the epilogue at compile time (the all-in-one epilogue was ~4000 SASS instructions of mutually exclusive paths;
+// the event trace showed ~900 cycles per 32-column chunk for ~100 useful instructions - instruction fetch, not math):
+//   0 generic (every combination, plain-store fallbacks)   1 Y only, through TMA (bias / ReLU; residual only with RTMA)
+//   2 Yhi / Ylo only, through TMA                          3 Ythi / Ytlo only (transposed split outputs, direct stores)
+template <int PAIR, int RTMA, int OUTK>
 __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_a2,
                                                                       const __grid_constant__ CUtensorMap map_bhi,
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         if (lane == 0) mbar_arrive(&bars->empty[s]);           // this warp is done with the smem A tile
         mbar_wait(&bars->a_empty[s], ph ^ 1);
         tc_fence_after();
+        if (warp == 8 && lane == 0) OG_TRACE_EVT(7, it);
         const uint32_t taddr = tmem + lane_base + COL_A + s * 64;
         tmem_st_32x32(taddr, hi);
         tmem_st_32x32(taddr + 32, lo);
@@ -227,7 +232,6 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
     const int trow = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int wg_tid = threadIdx.x & 127;
-    int nstore = 0;                                            // staged stores issued by this warpgroup so far
     const bool vec_r = a.R && (a.ldr % 4 == 0) && (a.strideR % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
     int g = 0, ntile = 0;
     for (int t = g_first; t < sc.ngroups; t += g_stride, ++ntile) {
@@ -235,6 +239,12 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
       float racc[HN];
 #pragma unroll
       for (int j = 0; j < HN; ++j) racc[j] = 0.f;
+      const int pb = ntile & 1;
+      {                                                        // global-load latency hides behind the main loop
+        const int c = half * HN + (wg_tid & 63), col = n0 + c;
+        if (wg_tid < 64) bars->bias[pb][c] = (a.bias && col < a.nout) ? __ldg(a.bias + col) : 0.f;
+        else             bars->rscale[pb][c] = (a.rscale && col < a.nout) ? __ldg(a.rscale + col) : 1.f;
+      }
       if (r_tma && wg_tid == 0) {
         // residual tile of this warpgroup's 64 columns -> its two staging buffers, in flight during the whole main loop
         // (per-thread row loads of R cost what the per-thread row stores did: ~1/3 of the tile time on the fc.3 GEMM)
@@ -261,18 +271,35 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         if (warp == 0 && lane == 0) OG_TRACE_EVT(6, g);
       }
       // ---- epilogue for this tile (overlaps the next tile's first chunks)
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(8, ntile);
+      constexpr bool GEN = OUTK == 0;
+      const bool has_y = GEN ? a.Y != nullptr : OUTK == 1, has_yhi = GEN ? a.Yhi != nullptr : OUTK == 2;
+      const bool has_yt = GEN && a.Yt != nullptr, has_ythi = GEN ? a.Ythi != nullptr : OUTK == 3;
+      const bool use_tma = GEN ? y_tma != 0 : OUTK != 3;
       const int grow = m0 + trow;
       const bool row_ok = grow < a.rows;
-      const float* Rrow = a.R ? a.R + (int64_t)bz * a.strideR + (int64_t)grow * a.ldr : nullptr;
+      const float* Rrow = (GEN && !r_tma && a.R) ? a.R + (int64_t)bz * a.strideR + (int64_t)grow * a.ldr : nullptr;
       const int64_t yoff = (int64_t)bz * a.strideY + (int64_t)grow * a.ldy;
       const int64_t ytoff = (int64_t)bz * a.strideYt + grow;
-      // stage this tile's bias / residual scale once (one element per thread) instead of 128 loads per thread
-      asm volatile("bar.sync 1, 256;" ::: "memory");            // previous tile's readers (both halves) are done
-      if (half == 0) {
-        bars->bias[trow] = (a.bias && n0 + trow < a.nout) ? __ldg(a.bias + n0 + trow) : 0.f;
-        bars->rscale[trow] = (a.rscale && n0 + trow < a.nout) ? __ldg(a.rscale + n0 + trow) : 1.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // One warpgroup barrier per tile makes the staged bias visible and tells everyone that the previous tile's TMA
+      // stores have finished reading the two staging buffers (they were issued a whole main loop ago).
+      if (wg_tid == 0 && !r_tma) tma_store_wait_read<0>();
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(9, ntile);
+      // staged stores are issued in groups of up to two buffers: fill, one fence + barrier, then the TMA stores
+      int npend = 0;
+      const CUtensorMap* pmap0 = nullptr; const CUtensorMap* pmap1 = nullptr; int pcol0 = 0, pcol1 = 0;
+      auto flush = [&]() {
+        if (npend == 0) return;
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        if (wg_tid == 0) {
+          tma_store_3d(pmap0, s_out + (half * 2 + 0) * OUT_TILE, pcol0, m0, bz);
+          if (npend == 2) tma_store_3d(pmap1, s_out + (half * 2 + 1) * OUT_TILE, pcol1, m0, bz);
+          tma_store_commit();
+        }
+        npend = 0;
+      };
 #pragma unroll
       for (int cc = 0; cc < HN / 32; ++cc) {                   // 32-column chunks of this warpgroup's half
         const int cl = half * HN + cc * 32;                    // column inside the tile
@@ -281,7 +308,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[cl + j]);
+          const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[pb][cl + j]);
           y[j] = fmaf(racc[cc * 32 + j], a.alpha, bv.x);         y[j + 1] = fmaf(racc[cc * 32 + j + 1], a.alpha, bv.y);
           y[j + 2] = fmaf(racc[cc * 32 + j + 2], a.alpha, bv.z); y[j + 3] = fmaf(racc[cc * 32 + j + 3], a.alpha, bv.w);
         }
@@ -290,13 +317,12 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
           for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (r_tma) {                                           // residual chunk cc sits (swizzled) in staging buffer cc
-          if (cc == 0) mbar_wait(&bars->r_full[half], ntile & 1);
-          nstore = cc;                                         // ... and the result goes back out through the same buffer
+          if (cc == 0) mbar_wait(&bars->r_full[half], ntile & 1);   // ... and the result goes back out through the same buffer
           const uint8_t* rsrc = s_out + (half * 2 + cc) * OUT_TILE + trow * 128;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 r = *reinterpret_cast<const float4*>(rsrc + ((c4 ^ (trow & 7)) * 16));
-            const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl + 4 * c4]);
+            const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[pb][cl + 4 * c4]);
             y[4 * c4] = fmaf(sv.x, r.x, y[4 * c4]);         y[4 * c4 + 1] = fmaf(sv.y, r.y, y[4 * c4 + 1]);
             y[4 * c4 + 2] = fmaf(sv.z, r.z, y[4 * c4 + 2]); y[4 * c4 + 3] = fmaf(sv.w, r.w, y[4 * c4 + 3]);
           }
@@ -305,17 +331,17 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 r = *reinterpret_cast<const float4*>(Rrow + cb + j);
-              const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[cl + j]);
+              const float4 sv = *reinterpret_cast<const float4*>(&bars->rscale[pb][cl + j]);
               y[j] = fmaf(sv.x, r.x, y[j]); y[j + 1] = fmaf(sv.y, r.y, y[j + 1]);
               y[j + 2] = fmaf(sv.z, r.z, y[j + 2]); y[j + 3] = fmaf(sv.w, r.w, y[j + 3]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (cb + j < a.nout) y[j] = fmaf(bars->rscale[cl + j], Rrow[cb + j], y[j]);
+            for (int j = 0; j < 32; ++j) if (cb + j < a.nout) y[j] = fmaf(bars->rscale[pb][cl + j], Rrow[cb + j], y[j]);
           }
         }
         // transposed outputs: for a fixed column the 32 lanes write 32 consecutive rows (already coalesced)
-        if (a.Yt && row_ok) {
+        if (has_yt && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (cb + j < a.nout) a.Yt[ytoff + (int64_t)(cb + j) * a.ldyt] = y[j];
         }
@@ -323,40 +349,42 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
         // segments per row, clipped to the tensor bounds); measured before: per-thread row stores took ~10K of the
         // ~16K cycles per tile.
         auto stage_store = [&](const CUtensorMap* map, const uint32_t (&v)[32]) {
-          uint8_t* buf = s_out + (half * 2 + (nstore & 1)) * OUT_TILE;
-          if (wg_tid == 0 && !r_tma) tma_store_wait_read<1>(); // the store that last read this buffer is done with it
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-          uint8_t* dst = buf + trow * 128;
+          if (npend == 2) {                                    // both buffers hold unsent data: send, then wait until they were read
+            flush();
+            if (wg_tid == 0) tma_store_wait_read<0>();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          }
+          if (warp == 0 && lane == 0) OG_TRACE_EVT(10 + cc, ntile);
+          uint8_t* dst = s_out + (half * 2 + npend) * OUT_TILE + trow * 128;     // r_tma: npend == cc, the residual chunk's own buffer
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(dst + ((c ^ (trow & 7)) * 16)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          fence_proxy_async();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-          if (wg_tid == 0) { tma_store_3d(map, buf, cb, m0, bz); tma_store_commit(); }
-          ++nstore;
+          if (npend == 0) { pmap0 = map; pcol0 = cb; } else { pmap1 = map; pcol1 = cb; }
+          ++npend;
+          if (warp == 0 && lane == 0) OG_TRACE_EVT(12 + cc, ntile);
         };
-        if (y_tma) {
-          if (a.Y) {
+        if (use_tma) {
+          if (has_y) {
             uint32_t v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(y[j]);
             stage_store(&map_y, v);
           }
-          if (a.Yhi) {
+          if (has_yhi) {
             uint32_t yh[32], yl[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) split_tf32(y[j], yh[j], yl[j]);
             stage_store(&map_yhi, yh);
             stage_store(&map_ylo, yl);
           }
-        } else if (row_ok) {                                   // unaligned row pitch: plain stores
+        } else if (GEN && row_ok) {                            // unaligned row pitch: plain stores
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
-            if (a.Y) a.Y[yoff + cb + j] = y[j];
-            if (a.Yhi) { uint32_t h, l; split_tf32(y[j], h, l); a.Yhi[yoff + cb + j] = __uint_as_float(h); a.Ylo[yoff + cb + j] = __uint_as_float(l); }
+            if (has_y) a.Y[yoff + cb + j] = y[j];
+            if (has_yhi) { uint32_t h, l; split_tf32(y[j], h, l); a.Yhi[yoff + cb + j] = __uint_as_float(h); a.Ylo[yoff + cb + j] = __uint_as_float(l); }
           }
         }
-        if (a.Ythi && row_ok) {
+        if (has_ythi && row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (cb + j < a.nout) {
             uint32_t h, l; split_tf32(y[j], h, l);
@@ -365,6 +393,8 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
           }
         }
       }
+      flush();
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(14, ntile);
     }
     if (wg_tid == 0) tma_store_wait_all<0>();                  // smem must outlive the last store's reads
   }
@@ -409,12 +439,23 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   CUtensorMap mr = ma;
   const int r_tma = y_tma && a.R && a.Y && !a.Yhi && a.ldr % 4 == 0 && a.strideR % 4 == 0 && al16(a.R) && a.nout % 32 == 0;
   if (r_tma && (rc = tc::make_tmap_3d(&mr, a.R, a.batch, a.rows, a.nout, a.ldr, a.strideR, BM)) != OG_OK) return rc;
+  // epilogue specialisation (see the kernel's OUTK): everything else takes the generic instantiation
+  int outk = 0;
+  if (!a.Yt && (r_tma || !a.R)) {
+    if (y_tma && a.Y && !a.Yhi && !a.Ythi) outk = 1;
+    else if (y_tma && !a.Y && a.Yhi && !a.Ythi) outk = 2;
+    else if (!a.Y && !a.Yhi && a.Ythi) outk = 3;
+  }
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                        TcLinearArgs, Sched, int);
+  static const Kern kerns[5] = {linear_tc2_kernel<PAIR, 0, 0>, linear_tc2_kernel<PAIR, 0, 1>, linear_tc2_kernel<PAIR, 0, 2>,
+                                linear_tc2_kernel<PAIR, 0, 3>, linear_tc2_kernel<PAIR, 1, 1>};
   static bool attr_set = false;
   if (!attr_set) {
-    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    OG_CUDA(cudaFuncSetAttribute(linear_tc2_kernel<PAIR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    for (Kern k : kerns) OG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
+  const Kern kern = r_tma ? kerns[4] : kerns[outk];
   Sched sc;
   sc.ntmg = cdiv(cdiv(a.rows, BM), NC); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
   sc.nkb = cdiv(K, BK); sc.nchunks = cdiv(sc.nkb, CHUNK_KB);
@@ -429,17 +470,17 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (r_tma) { OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR, 1>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma)); }
-  else       { OG_CUDA(cudaLaunchKernelEx(&cfg, linear_tc2_kernel<PAIR, 0>, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma)); }
+  OG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma));
   launch_counter()++;
   return OG_OK;
 }
 
-// OG_GEMM_PAIR=1 selects the cta_group::2 form.  Parity-clean, but measured SLOWER on B200 (137 vs 186 TF/s on the
-// QKV shape; event trace: ~1850 vs ~1400 cycles per K block): the M = 256 MMAs take about twice as long per
-// instruction, so the halved smem traffic buys nothing, and the cross-CTA barrier hops add latency.  Default 0.
+// The cta_group::2 form is the default (OG_GEMM_PAIR=0 / og_set_tuning select the single-CTA form; both parity-tested).
+// Event traces: single CTA ~1400 cycles per K block (128 KB of shared-memory traffic each), pair ~1050 (88 KB) against 768 of
+// MMA work.  An earlier measurement had the pair SLOWER (137 vs 186 TF/s): the peer CTA's hand-offs used
+// mbarrier.arrive.release.cluster, which cost ~1000+ cycles each; with the default-semantics remote arrive they are ~free.
 inline int& linear_tc2_pair_mode() {
-  static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+  static int v = [] { const char* e = getenv("OG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   return v;
 }
 

@@ -7,9 +7,9 @@
 
 namespace og {
 #ifdef OG_TRACE
-// debug build only (scripts/trace_*.py): event timestamps of CTA 0
-__device__ long long og_trace_buf[8 * 256];
-#define OG_TRACE_EVT(ev, idx) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 256) og_trace_buf[(ev) * 256 + (idx)] = clock64(); } while (0)
+// debug build only (scripts/trace_*.py): event timestamps of CTAs 0 and 1 (a cta_group::2 pair)
+__device__ long long og_trace_buf[2 * 16 * 256];
+#define OG_TRACE_EVT(ev, idx) do { if (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 256) og_trace_buf[blockIdx.x * 4096 + (ev) * 256 + (idx)] = clock64(); } while (0)
 #else
 #define OG_TRACE_EVT(ev, idx) do { } while (0)
 #endif
@@ -104,7 +104,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  // default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): everything handed over through
+  // these barriers lives in TMEM and is ordered by tcgen05.wait + tcgen05.fence.  A .release.cluster here made every
+  // hand-off wait ~1000+ cycles (event trace: the peer CTA's converters took 1500-2200 cycles per K block against 450 in the leader).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
 // ---- CTA pairs (cta_group::2): one MMA spans two SMs (M = 256, each CTA holds half of B's N rows) ----

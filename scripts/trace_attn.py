@@ -22,7 +22,7 @@ for _ in range(3):
                                  I(nb), I(n), I(n), I(H), I(d // H), st)
     assert rc == 0, rc
 torch.cuda.synchronize()
-buf = (C.c_longlong * (8 * 256))()
+buf = (C.c_longlong * (2 * 16 * 256))()
 assert lib.og_trace_read(buf) == 0
 ev = [[buf[e * 256 + i] for i in range(256)] for e in range(8)]
 t0 = ev[1][0]

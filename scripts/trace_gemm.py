@@ -26,14 +26,21 @@ for _ in range(3):
     rc = lib.og_linear_tc_fwd(C.byref(a), p(Whi), p(Wlo), None, None, None, None, 2, st)
     assert rc == 0, rc
 torch.cuda.synchronize()
-buf = (C.c_longlong * (8 * 256))()
+buf = (C.c_longlong * (2 * 16 * 256))()
 assert lib.og_trace_read(buf) == 0
-ev = [[buf[e * 256 + i] for i in range(256)] for e in range(8)]
-t0 = ev[0][0]
-print('kb   issue   conv_full conv_done  mma_full  mma_issue | d(issue) d(mma_issue)')
-for i in range(8, 72):
-    r = [ev[e][i] - t0 for e in range(5)]
-    print(f'{i:3d} {r[0]:8d} {r[1]:9d} {r[2]:9d} {r[3]:9d} {r[4]:9d} | {ev[0][i]-ev[0][i-1]:6d} {ev[4][i]-ev[4][i-1]:6d}   tma_lat={ev[1][i]-ev[0][i]:6d} conv={ev[2][i]-ev[1][i]:5d} mma_wait_after_conv={ev[4][i]-ev[2][i]:6d}')
-print('chunks: acc_full seen, drained (delta to previous)')
-for g in range(4, 36):
-    print(g, ev[5][g] - t0, ev[6][g] - ev[5][g], ev[5][g] - ev[5][g - 1])
+for cta in range(1 if os.environ.get('OG_GEMM_PAIR') == '0' else 2):
+    ev = [[buf[cta * 4096 + e * 256 + i] for i in range(256)] for e in range(16)]
+    t0 = ev[0][0]
+    print(f'=== CTA {cta} (clock64 of its own SM)')
+    print('kb   issue   a_land  a_empty_ok conv_done  mma_bfull mma_afull | d(issue) d(mma)  tma_lat  split+wait  st+arrive  conv_done->mma')
+    for i in range(8, 72):
+        r = [ev[e][i] - t0 for e in range(8)]
+        print(f'{i:3d} {r[0]:8d} {r[1]:8d} {r[7]:9d} {r[2]:9d} {r[3]:9d} {r[4]:9d} | {ev[0][i]-ev[0][i-1]:6d} {ev[4][i]-ev[4][i-1]:6d}   '
+              f'{ev[1][i]-ev[0][i]:6d} {ev[7][i]-ev[1][i]:8d} {ev[2][i]-ev[7][i]:8d} {ev[4][i]-ev[2][i]:10d}')
+    print('chunks: acc_full seen, drained (delta to previous)')
+    for g in range(4, 36):
+        print(g, ev[5][g] - t0, ev[6][g] - ev[5][g], ev[5][g] - ev[5][g - 1])
+    print('epilogue of warp 0 per tile (cycles after its start): barrier passed | cc0: enter staging, staged | cc1: same | stores issued')
+    for t in range(1, 12):
+        e = lambda k: ev[k][t] - ev[8][t]
+        print(f'{t:3d} start={ev[8][t]-t0:8d} bar={e(9):5d} | cc0 {e(10):5d} {e(12):5d} | cc1 {e(11):5d} {e(13):5d} | end {e(14):5d}')

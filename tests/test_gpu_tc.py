@@ -86,15 +86,15 @@ def test_attention_tc_operator(B, H, dh, nq, nk):
     assert (out.cpu().double() - ref).abs().max() <= 1e-5 * ref.abs().max()
 
 
-@pytest.fixture
-def paired_kernels():
-    """Run a test with the cta_group::2 (CTA pair) forms of the GEMM and attention kernels."""
+@pytest.fixture(params=[0, 1], ids=['single_cta', 'cta_pair'])
+def kernel_form(request):
+    """Run a test with the single-CTA or the cta_group::2 (CTA pair, default) forms of the GEMM and attention kernels."""
+    _cabi.check(_cabi.lib().og_set_tuning(request.param, request.param), 'og_set_tuning')
+    yield request.param
     _cabi.check(_cabi.lib().og_set_tuning(1, 1), 'og_set_tuning')
-    yield
-    _cabi.check(_cabi.lib().og_set_tuning(0, 0), 'og_set_tuning')
 
 
-def test_paired_kernel_forms_match_reference(golden, paired_kernels):
+def test_both_kernel_forms_match_reference(golden, kernel_form):
     for name in ('small_planted', 'C1_planted'):
         test_forward_tf32x3_matches_reference(golden, name)
     test_attention_tc_operator(2, 4, 64, 200, 333)
