@@ -77,11 +77,12 @@ def lib() -> C.CDLL:
     """Load (once) and return the shared library; raise if it is not built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get('OG_LIB') or LIB_PATH     # OG_LIB: an experimental build of the same sources (A/B timing)
+        if not os.path.exists(path):
             raise OpenGlueB200Error(
-                f'{LIB_PATH} is missing: build it with `python -m openglue_b200.build` '
+                f'{path} is missing: build it with `python -m openglue_b200.build` '
                 '(there is no fallback implementation)')
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args

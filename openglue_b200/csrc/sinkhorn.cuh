@@ -34,11 +34,12 @@ struct SinkArgs {
   float* scores;                         // [B, n+1, m+1]
   float* u;                              // [B, n+1]   workspace
   float* partial;                        // [2, B, SP, mpad] workspace
-  unsigned int* barrier;                 // zeroed before launch
+  unsigned int* barrier;                 // [B] counters, one per pair, 128 bytes apart; zeroed before launch
   int SP, rows_per_strip, mpad;
 };
 
 constexpr int SINK_WARPS = 8;
+constexpr int64_t SINK_BARRIER_BYTES = 256 * 128;     // one 128-byte line per pair of a launch (<= SM count pairs)
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
@@ -79,8 +80,10 @@ template <int V>
 __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a) {
   extern __shared__ __align__(128) float og_sink_smem[];
   constexpr int SLOT = 128 * V;                        // floats per ring slot (one padded row)
-  float* v_s = og_sink_smem;                           // [mpad]   v_j, j = 0..m (m = dustbin column)
-  float* red = og_sink_smem + a.mpad;                  // [SINK_WARPS][mpad]
+  constexpr int VD = 128 * V;                          // v_s[VD] = v of the dustbin column
+  float* v_s = og_sink_smem;                           // [128 V + 4]  v_j for j < m, -inf for m <= j < 128 V (masks the padding
+                                                       //              columns in the sweep without per-element selects), v_dustbin
+  float* red = og_sink_smem + VD + 4;                  // [SINK_WARPS][mpad]
   float* ring = red + SINK_WARPS * a.mpad;             // [SINK_WARPS][SINK_SLOTS][SLOT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SINK_WARPS * SINK_SLOTS * SLOT);   // [SINK_WARPS][SINK_SLOTS]
   const int b = blockIdx.x / a.SP, strip = blockIdx.x % a.SP;
@@ -101,7 +104,8 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
     for (int sl = 0; sl < SINK_SLOTS; ++sl) sink_mbar_init(&my_bars[sl]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int j = tid; j <= m; j += blockDim.x) v_s[j] = 0.f;
+  for (int j = tid; j < VD; j += blockDim.x) v_s[j] = (j < m) ? 0.f : -CUDART_INF_F;
+  if (tid == 0) v_s[VD] = 0.f;
   __syncthreads();
 
   uint32_t issued = 0, consumed = 0;                   // per-warp ring counters (real rows only)
@@ -124,6 +128,17 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
       for (int k = 0; k < V; ++k) {
         const int idx = lane + 32 * k;
         z[k] = (4 * idx < m) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (m & 3) {                                     // the float4 that straddles column m: its tail is row padding (any bits)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const int c = 4 * (lane + 32 * k);
+          if (c < m && c + 3 >= m) {
+            if (c + 1 >= m) z[k].y = 0.f;
+            if (c + 2 >= m) z[k].z = 0.f;
+            z[k].w = 0.f;
+          }
+        }
       }
       ++consumed;
       __syncwarp();                                    // every lane has its part of the row in registers
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
 #pragma unroll
     for (int k = 0; k < V; ++k) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     float cacc_m = 0.f;
-    const float v_m = v_s[m];
+    const float v_m = v_s[VD];
 
     for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
       float4 z[V];
@@ -162,11 +177,8 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const int c = 4 * (lane + 32 * k);
-        const float4 vv = *reinterpret_cast<const float4*>(v_s + c);   // c < mpad always
-        z[k].x = (c + 0 < m) ? z[k].x + vv.x : -CUDART_INF_F;
-        z[k].y = (c + 1 < m) ? z[k].y + vv.y : -CUDART_INF_F;
-        z[k].z = (c + 2 < m) ? z[k].z + vv.z : -CUDART_INF_F;
-        z[k].w = (c + 3 < m) ? z[k].w + vv.w : -CUDART_INF_F;
+        const float4 vv = *reinterpret_cast<const float4*>(v_s + c);   // columns >= m: finite z + (-inf) = -inf, e = 0
+        z[k].x += vv.x; z[k].y += vv.y; z[k].z += vv.z; z[k].w += vv.w;
         mx = fmaxf(mx, fmaxf(fmaxf(z[k].x, z[k].y), fmaxf(z[k].z, z[k].w)));
       }
       mx = warp_max(mx);
@@ -209,21 +221,33 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
       for (int w = 0; w < SINK_WARPS; ++w) s += red[w * a.mpad + j];
       part[j] = s;
     }
-    grid_barrier(a.barrier, (unsigned int)(it + 1) * gridDim.x);
+    // only the SP CTAs of this pair exchange data: a per-pair barrier (own 128-byte line) lets the pairs drift apart,
+    // so HBM keeps streaming for the other pairs while one pair sits in its reduction / barrier phase
+    grid_barrier(a.barrier + 32 * b, (unsigned int)(it + 1) * (unsigned int)a.SP);
     // every CTA of the pair rebuilds v (fixed summation order => bitwise identical across CTAs)
     const float* pb = a.partial + ((int64_t)(it & 1) * a.B * a.SP + (int64_t)b * a.SP) * a.mpad;
-    for (int j = tid; j <= m; j += blockDim.x) {
-      float c = 0.f;
-      for (int s = 0; s < a.SP; ++s) c += __ldcg(pb + (int64_t)s * a.mpad + j);
-      const float log_b = (j < m) ? a.norm : a.log_b_last;
-      v_s[j] = log_b + v_s[j] - logf(c);
+    // float4 columns, all SP loads of a thread in flight together (this phase is pure L2 latency: every CTA of the pair waits on it)
+    for (int j4 = tid; 4 * j4 <= m; j4 += blockDim.x) {
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int s = 0; s < a.SP; ++s) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(pb + (int64_t)s * a.mpad) + j4);
+        c.x += q.x; c.y += q.y; c.z += q.z; c.w += q.w;
+      }
+      const float cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * j4 + e;
+        if (j < m) v_s[j] = a.norm + v_s[j] - logf(cc[e]);
+        else if (j == m) v_s[VD] = a.log_b_last + v_s[VD] - logf(cc[e]);
+      }
     }
     __syncthreads();
   }
 
   // final pass: scores = Z + u + v - norm   (optimal_transport.py:28, superglue.py:111)
   {
-    const float v_m = v_s[m];
+    const float v_m = v_s[VD];
     for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
       float4 z[V];
       take_row(row, z);
@@ -255,7 +279,7 @@ inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
   if (m <= 512) p->V = 4; else if (m <= 1024) p->V = 8; else if (m <= 2048) p->V = 16;
   else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > 2048 columns not supported (swap the images)", m);
   const int sms = device_info().ok ? device_info().sm_count : 148;
-  p->pairs_per_launch = B < sms ? B : sms;
+  p->pairs_per_launch = std::min(B < sms ? B : sms, (int)(SINK_BARRIER_BYTES / 128));
   // experiment knobs: OG_SINK_PAIRS = pairs per launch (L2 blocking), OG_SINK_SP = max strips per pair
   static const int env_pairs = [] { const char* e = getenv("OG_SINK_PAIRS"); return e ? atoi(e) : 0; }();
   static const int env_sp = [] { const char* e = getenv("OG_SINK_SP"); return e ? atoi(e) : 16; }();
@@ -271,7 +295,7 @@ inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
   if (p->mpad < 128 * p->V) {                      // v_s is read as float4 up to column 128 V - 1
     // only columns < m are ever used, but the smem reads must stay in bounds
   }
-  p->smem = ((size_t)(1 + SINK_WARPS) * (size_t)std::max(p->mpad, 128 * p->V) + (size_t)SINK_WARPS * SINK_SLOTS * 128 * p->V) * sizeof(float) +
+  p->smem = ((size_t)(128 * p->V + 4) + (size_t)SINK_WARPS * (size_t)std::max(p->mpad, 128 * p->V) + (size_t)SINK_WARPS * SINK_SLOTS * 128 * p->V) * sizeof(float) +
             (size_t)SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128;
   return OG_OK;
 }
@@ -280,7 +304,7 @@ inline int64_t sinkhorn_workspace_bytes(int B, int n, int m) {
   SinkPlan p;
   if (sinkhorn_plan(B, n, m, &p) != OG_OK) return -1;
   const int64_t mp = std::max(p.mpad, 128 * p.V);
-  return align_up(256, 256) + align_up((int64_t)B * (n + 1) * 4, 256) + align_up(2LL * B * p.SP * mp * 4, 256);
+  return SINK_BARRIER_BYTES + align_up((int64_t)B * (n + 1) * 4, 256) + align_up(2LL * B * p.SP * mp * 4, 256);
 }
 
 template <int V>
@@ -316,7 +340,7 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
     return fail(OG_EINVAL, "sinkhorn: S rows must be 16-byte aligned (lds %% 4 == 0, lds >= m)");
   const int64_t mp = std::max(p.mpad, 128 * p.V);
   char* w = static_cast<char*>(ws);
-  unsigned int* barrier = reinterpret_cast<unsigned int*>(w); w += 256;
+  unsigned int* barrier = reinterpret_cast<unsigned int*>(w); w += SINK_BARRIER_BYTES;
   float* u = reinterpret_cast<float*>(w); w += align_up((int64_t)B * (n + 1) * 4, 256);
   float* partial = reinterpret_cast<float*>(w);
   // host-side constants exactly as the reference builds them (float32 throughout)
@@ -332,7 +356,7 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
     a.scores = scores + (int64_t)b0 * (n + 1) * (m + 1);
     a.u = u; a.partial = partial; a.barrier = barrier;
     a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = (int)mp;
-    OG_CUDA(cudaMemsetAsync(barrier, 0, 256, stream));
+    OG_CUDA(cudaMemsetAsync(barrier, 0, (size_t)nb * 128, stream));
     switch (p.V) {
       case 4:  rc = sinkhorn_launch_v<4>(a, p, stream); break;
       case 8:  rc = sinkhorn_launch_v<8>(a, p, stream); break;

@@ -248,7 +248,11 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 __device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   const float r = x - __uint_as_float(hi);
+#ifdef OG_SPLIT_LO_RAW
+  lo = __float_as_uint(r);      // experiment: let the tensor core drop the 13 low bits of lo itself (<= 2^-22 |x| instead of 2^-23)
+#else
   lo = (__float_as_uint(r) + 0x1000u) & 0xFFFFE000u;
+#endif
 }
 
 // ----------------------------------------------------------------------------- host: tensor maps

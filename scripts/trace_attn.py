@@ -24,9 +24,16 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = (C.c_longlong * (2 * 16 * 256))()
 assert lib.og_trace_read(buf) == 0
+pair = os.environ.get('OG_ATTN_PAIR') != '0'
 ev = [[buf[e * 256 + i] for i in range(256)] for e in range(8)]
 t0 = ev[1][0]
-print('blk  waitK  issQK | waitP  Pready issPV | S_seen P_given O_folded || softmax_lat  P_wait  dPV')
-for i in range(2, 30):
+print('leader CTA   blk  waitK  issQK | waitP  Pready issPV | S_seen P_given O_folded || softmax_lat  P_wait  dQK   dPV   S_seen-issQK  issPV-P_given')
+for i in range(4, 40):
     r = [ev[e][i] - t0 for e in range(8)]
-    print(f'{i:3d} {r[0]:6d} {r[1]:6d} | {r[2]:6d} {r[3]:6d} {r[4]:6d} | {r[5]:6d} {r[6]:6d} {r[7]:6d} || {ev[6][i]-ev[5][i]:6d} {ev[3][i]-ev[2][i]:6d} {ev[4][i]-ev[4][i-1]:6d}')
+    print(f'{i:3d} {r[0]:6d} {r[1]:6d} | {r[2]:6d} {r[3]:6d} {r[4]:6d} | {r[5]:6d} {r[6]:6d} {r[7]:6d} || {ev[6][i]-ev[5][i]:6d} {ev[3][i]-ev[2][i]:6d} '
+          f'{ev[1][i]-ev[1][i-1]:6d} {ev[4][i]-ev[4][i-1]:6d}   {ev[5][i]-ev[1][i]:6d} {ev[4][i]-ev[6][i]:6d}')
+if pair:
+    ev1 = [[buf[4096 + e * 256 + i] for i in range(256)] for e in range(8)]
+    print('peer CTA (its own clock): S_seen P_given O_folded | softmax_lat  d(S_seen)')
+    for i in range(4, 40):
+        print(f'{i:3d} {ev1[5][i]-ev1[5][4]:7d} {ev1[6][i]-ev1[5][4]:7d} {ev1[7][i]-ev1[5][4]:7d} | {ev1[6][i]-ev1[5][i]:6d} {ev1[5][i]-ev1[5][i-1]:6d}')
