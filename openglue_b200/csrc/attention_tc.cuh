@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   constexpr int K_HALF = (DH / 32) * KBLK;        // hi (or lo) part of a K stage
   constexpr int V_HALF = 2 * VBLK;
 
+  launch_dependents();                                       // the next kernel may take this SM as soon as this CTA leaves it
   extern __shared__ uint8_t og_tca_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tca_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  grid_dependency_wait();                                    // nothing above touches memory written by the previous kernel
   // signal a barrier that lives in the leader CTA (local arrive for CG = 1 / the leader itself)
   // (one lane per warp, after every lane of the warp has completed and fenced its own TMEM accesses)
   auto arrive_leader = [&](uint64_t* bar) {
@@ -418,10 +420,12 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem_bytes<DH, CG>();
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tc::pdl_mode() ? 2 : 1;
   OG_CUDA(cudaLaunchKernelEx(&cfg, attention_tc_kernel<DH, CG>, mkh, mkl, mvh, mvl, ap));
   launch_counter()++;
   return OG_OK;

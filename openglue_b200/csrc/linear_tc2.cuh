@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   using namespace tc;
   using C = Cfg<PAIR>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE = C::B_TILE, NC = PAIR ? 2 : 1;
+  launch_dependents();                                       // the next kernel may take this SM as soon as this CTA leaves it
   extern __shared__ uint8_t og_tcl2_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl2_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;                          // [2 warpgroups][2 buffers][16 KB]
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  grid_dependency_wait();                                    // nothing above touches memory written by the previous kernel
   // one arrival per warp (after every lane has completed and fenced its own TMEM / smem accesses) on a barrier that
   // lives in the leader CTA
   auto arrive_leader = [&](uint64_t* bar) {
@@ -466,10 +468,12 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tc::pdl_mode() ? 2 : 1;
   OG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mhi, mlo, my, myh, myl, mr, a, sc, y_tma));
   launch_counter()++;
   return OG_OK;

@@ -2,6 +2,7 @@
 // tcgen05 (TMEM alloc / ld / st / mma / commit), UMMA descriptors, tf32 hi/lo split.
 // Descriptor bit layouts follow the PTX ISA (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include <cuda.h>
 
@@ -94,6 +95,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the previous kernel
+// of the stream is still draining: launch_dependents (issued at the very top) lets the NEXT kernel's CTAs take an SM as soon
+// as this kernel's CTA leaves it, and grid_dependency_wait blocks until the PREVIOUS kernel has completed and flushed its
+// writes.  Everything before the wait (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail.
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline int& pdl_mode() {
+  static int v = [] { const char* e = getenv("OG_PDL"); return e ? atoi(e) : 1; }();
+  return v;
+}
 
 // ----------------------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
