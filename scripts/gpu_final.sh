@@ -1,5 +1,6 @@
 #!/bin/bash
-# Full validation visit: all GPU tests, smoke, headline bench (+cpu baseline), other configs, ncu evidence.
+# Full validation visit: all GPU tests, smoke, headline bench (+cpu baseline), reference arm, other configs.
+cd "$GRAFT_REPO_ROOT" || exit 1
 set +e
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -8 > gpurun_out/pytest_gpu.log
@@ -7,10 +8,8 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 for wl in C1 C2 C5; do
-  timeout 600 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
+  timeout 600 python bench.py --workload $wl --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 1 -c 1 -o gpurun_out/prof_attn4 -f python scripts/prof_ops.py attn 2 > gpurun_out/prof_attn.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -2
 python - <<'PY'
 import json
