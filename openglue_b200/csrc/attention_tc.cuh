@@ -46,7 +46,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 struct __align__(8) Barriers {
   uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2], plo_free[2];
   uint32_t tmem_base;
 };
 // CG = 1: one CTA per 128 queries.  CG = 2: a CTA pair (cta_group::2) per 256 queries; every MMA spans both SMs
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     mbar_init(&bars->q_free, 1);                     // every QK^T of the current tile has retired: Q may be replaced
     for (int j = 0; j < 2; ++j) {
       mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 8 * CG);
-      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG);
+      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG); mbar_init(&bars->plo_free[j], 1);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
@@ -183,12 +183,14 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
         OG_TRACE_EVT(0, i);
         mbar_wait(&bars->k_full[s], ph);
-        if (i >= 2) mbar_wait(&bars->o_full[j], ((i - 2) >> 1) & 1);   // PV_{i-2} has consumed P_{i-2}: S/P buffer j is free
+        // S_i goes where P_lo of block i-2 was: P.V_{i-2} reads P_lo with its FIRST eight MMAs and signals plo_free, so this
+        // QK^T does not wait for the other sixteen (the per-buffer chain QK -> softmax -> P.V -> QK paces the kernel)
+        if (i >= 2) mbar_wait(&bars->plo_free[j], ((i - 2) >> 1) & 1);
         tc_fence_after();
         OG_TRACE_EVT(1, i);
         if (elect_one()) {
           const uint32_t khi = smem_u32(sK + s * k_stage_bytes<DH, CG>()), klo = khi + K_HALF;
-          const uint32_t d_s = tmem + COL_SP + 128 * j;
+          const uint32_t d_s = tmem + COL_SP + 128 * j + 64 * ((i >> 1) & 1);     // the halves of an S/P buffer swap roles per use
 #pragma unroll
           for (int kk = 0; kk < DH / 8; ++kk) {
             const uint32_t off = (kk / 4) * KBLK + (kk % 4) * 32;
@@ -217,13 +219,19 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         OG_TRACE_EVT(4, i);
         if (elect_one()) {
           const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<DH, CG>()), vlo = vhi + V_HALF;
-          const uint32_t p_hi = tmem + COL_SP + 128 * j, p_lo = p_hi + 64;
+          const uint32_t hh = (i >> 1) & 1;
+          const uint32_t p_hi = tmem + COL_SP + 128 * j + 64 * hh, p_lo = tmem + COL_SP + 128 * j + 64 * (hh ^ 1);
           const uint32_t d_o = tmem + COL_O + 64 * j;
+#pragma unroll
+          for (int kk = 0; kk < BNK / 8; ++kk) {             // the P_lo readers first: their half is the next S accumulator
+            const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
+            mma(d_o, p_lo + kk * 8, make_sdesc_sw128(vhi + off), idesc_pv, kk ? 1u : 0u);
+          }
+          commit(&bars->plo_free[j]);
 #pragma unroll
           for (int kk = 0; kk < BNK / 8; ++kk) {
             const uint32_t off = (kk / 4) * VBLK + (kk % 4) * 32;
             const uint64_t dhi = make_sdesc_sw128(vhi + off), dlo = make_sdesc_sw128(vlo + off);
-            mma(d_o, p_lo + kk * 8, dhi, idesc_pv, kk ? 1u : 0u);
             mma(d_o, p_hi + kk * 8, dlo, idesc_pv, 1u);
             mma(d_o, p_hi + kk * 8, dhi, idesc_pv, 1u);
           }
@@ -326,7 +334,9 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     for (int iloc = 0; iloc < nblk; ++iloc, ++it) {
       const int i = it;                              // global block index
       const int j = i & 1, jph = (i >> 1) & 1;
-      const uint32_t sp = tmem + lane_base + COL_SP + 128 * j + 32 * g;      // my 32 columns of S_i / P_hi
+      const uint32_t hh = (i >> 1) & 1;              // which half of the buffer holds S_i / P_hi (the other one gets P_lo)
+      const uint32_t sp = tmem + lane_base + COL_SP + 128 * j + 64 * hh + 32 * g;      // my 32 columns of S_i / P_hi
+      const uint32_t sp_lo = tmem + lane_base + COL_SP + 128 * j + 64 * (hh ^ 1) + 32 * g;
       const int kbase = iloc * BNK + 32 * g;
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
@@ -356,8 +366,8 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
         split_tf32_fast(p0, s[c], lo[c]);
         split_tf32_fast(p1, s[c + 1], lo[c + 1]);
       }
-      tmem_st_32x32(sp, s);                          // P_hi over S, P_lo beside it
-      tmem_st_32x32(sp + 64, lo);
+      tmem_st_32x32(sp, s);                          // P_hi over S, P_lo into the other half (where P_hi of block i-2 was:
+      tmem_st_32x32(sp_lo, lo);                      // this thread has already waited for P.V_{i-2} in fold_o(i-2))
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->p_full[j]);
