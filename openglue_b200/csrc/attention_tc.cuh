@@ -44,7 +44,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int COL_QHI = 0, COL_QLO = 64, COL_SP = 128, COL_O = 384;
 constexpr float LOG2E = 1.4426950408889634f;
 
-struct __align__(8) Barriers {
+struct __align__(16) Barriers {      // 16: the staging tiles behind the exchange buffer are accessed as float4
   uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
   uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2], plo_free[2];
   uint32_t tmem_base;
@@ -53,8 +53,13 @@ struct __align__(8) Barriers {
 // (M = 256) and each CTA stages only half of the K rows / V^T channels of a block.
 template <int DH, int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * DH * 4; }        // hi + lo
 template <int DH, int CG> __host__ __device__ constexpr int v_stage_bytes() { return 2 * (DH / CG) * BNK * 4; }
+// CG = 2 has shared memory to spare: per softmax warp one [32 rows x Dh/2] staging tile for the next tile's Q rows and one for the
+// output rows, so that global loads / stores move whole 128-byte rows per instruction (a thread owns a row - TMEM lane - and
+// its own 128 bytes: 32 different cache lines per warp instruction, which cost ~2000 LSU cycles per tile each way)
+template <int DH, int CG> __host__ __device__ constexpr int stage_bytes() { return CG == 2 ? 2 * 8 * 32 * (DH / 2) * 4 : 0; }
 template <int DH, int CG> __host__ __device__ constexpr int smem_bytes() {
-  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512 + 8 * 128 * 4;
+  return 1024 + (STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>()) < 36864 ? 36864 : STAGES * (k_stage_bytes<DH, CG>() + v_stage_bytes<DH, CG>())) + 512 + 8 * 128 * 4 +
+         stage_bytes<DH, CG>();
 }
 }  // namespace tca
 
@@ -85,12 +90,20 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   const int nblk = (a.nk + BNK - 1) / BNK;
   const int t_first = blockIdx.x / CG, t_stride = gridDim.x / CG;      // tile list of this CTA (pair)
-  // tile t -> (query-block group, head, batch); query groups fastest so that co-running CTAs share K / V in L2
-  auto tile_coords = [&](int t, int& q0, int& h, int& b) {
-    q0 = ((t % a.nqg) * CG + (int)crank) * BM;
-    h = (t / a.nqg) % a.num_heads;
-    b = t / (a.nqg * a.num_heads);
+  // tile t -> (query-block group, head, batch); query groups fastest so that co-running CTAs share K / V in L2.
+  // The decomposition is advanced incrementally from tile to tile (t += t_stride): the integer divisions run once per
+  // kernel instead of three times per tile - once-per-tile code is instruction-cache-cold (ncu: ~130 instruction-cache
+  // misses per tile and SM; the tile hand-over cost ~9 % of a 32-block tile), so it is kept short.
+  struct TilePos { int qg, h, b; };
+  auto tile_pos = [&](int t) { TilePos p; p.qg = t % a.nqg; p.h = (t / a.nqg) % a.num_heads; p.b = t / (a.nqg * a.num_heads); return p; };
+  const TilePos t_step = tile_pos(t_stride);          // (b may exceed the batch here: it is only ever added)
+  auto tile_next = [&](TilePos p) {
+    p.qg += t_step.qg; if (p.qg >= a.nqg) { p.qg -= a.nqg; ++p.h; }
+    p.h += t_step.h;   if (p.h >= a.num_heads) { p.h -= a.num_heads; ++p.b; }
+    p.b += t_step.b;
+    return p;
   };
+  auto tile_q0 = [&](const TilePos& p) { return (p.qg * CG + (int)crank) * BM; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -127,8 +140,9 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;                                   // key blocks loaded so far (ring position), across tiles
-      for (int t = t_first; t < a.ntiles; t += t_stride) {
-      int q0, h, b; tile_coords(t, q0, h, b);
+      TilePos tp = tile_pos(t_first);
+      for (int t = t_first; t < a.ntiles; t += t_stride, tp = tile_next(tp)) {
+      const int h = tp.h, b = tp.b;
       const int krow0 = b * a.nk;                   // K rows of this batch item
       const int vrow = b * a.d + h * DH;            // V^T rows (channels) of this (batch, head)
       for (int i = 0; i < nblk; ++i, ++it) {
@@ -257,15 +271,39 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     const float c1 = a.scale * LOG2E;
     int it = 0, nt = 0;                              // key blocks / tiles done so far (buffer parities run across tiles)
     float4 qv[HD / 4];                               // this thread's half Q row of the NEXT tile to start
-    auto load_q = [&](int t) {
-      int q0, h, b; tile_coords(t, q0, h, b);
-      const int grow = q0 + trow;
-      const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH + g * HD;
+    constexpr bool STAGED = CG == 2;                 // row-coalesced global access through per-warp smem tiles (see stage_bytes)
+    constexpr int LPR = HD / 4, RPI = 32 / LPR;      // lanes per row / rows per warp instruction when a row is HD floats
+    float* qst = xch + 8 * 128 + warp * (2 * 32 * HD);   // this warp's Q staging tile [32][HD] (16-byte chunks XOR-swizzled by row)
+    float* ost = qst + 32 * HD;                      //             output staging tile
+    auto load_q = [&](const TilePos& p) {
+      const int h = p.h, b = p.b;
+      if constexpr (STAGED) {                        // cp.async: 8 (4) lanes fetch one row's 128 (64) bytes; lands during the tile
+        const int r_in = lane / LPR, ch = lane % LPR;
 #pragma unroll
-      for (int c = 0; c < HD / 4; ++c)
-        qv[c] = (grow < a.nq) ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < LPR; ++k) {
+          const int row = k * RPI + r_in, grow = tile_q0(p) + qd * 32 + row;
+          float* dst = qst + row * HD + ((ch ^ (row & (LPR - 1))) * 4);
+          const float* src = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH + g * HD + ch * 4;
+          if (grow < a.nq) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+          else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
+        const int grow = tile_q0(p) + trow;
+        const float* qrow = a.q + (int64_t)b * a.strideq + (int64_t)grow * a.ldq + h * DH + g * HD;
+#pragma unroll
+        for (int c = 0; c < HD / 4; ++c)
+          qv[c] = (grow < a.nq) ? __ldg(reinterpret_cast<const float4*>(qrow + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
     auto write_q = [&]() {                           // qv -> split -> TMEM (A operand of every QK^T of a tile)
+      if constexpr (STAGED) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < HD / 4; ++c) qv[c] = *reinterpret_cast<const float4*>(qst + lane * HD + ((c ^ (lane & (LPR - 1))) * 4));
+        __syncwarp();                                // the tile may be refilled by the next load_q
+      }
       if constexpr (HD == 32) {
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -289,15 +327,17 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       tc_fence_before();
       arrive_leader(&bars->q_ready);
     };
-    if (t_first < a.ntiles) load_q(t_first);
+    TilePos tp = tile_pos(t_first);
+    if (t_first < a.ntiles) load_q(tp);
 
 #pragma unroll 1
     for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
-    int q0, h, b; tile_coords(t, q0, h, b);
-    const int grow = q0 + trow;
+    const int h = tp.h, b = tp.b;
+    const int grow = tile_q0(tp) + trow;
     const bool row_ok = grow < a.nq;
+    tp = tile_next(tp);                              // from here on: the NEXT tile of this CTA
     if (nt == 0) write_q();                          // later tiles: written at the end of the previous tile (see below)
-    if (t + t_stride < a.ntiles) load_q(t + t_stride);   // next tile's Q row: in flight during this whole tile
+    if (t + t_stride < a.ntiles) load_q(tp);         // next tile's Q row: in flight during this whole tile
 
     float acc[HD];
 #pragma unroll
@@ -341,6 +381,14 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
       if (warp == 0 && lane == 0) OG_TRACE_EVT(5, i); // softmax: S_i observed
+      if (iloc == nblk - 1 && t + t_stride < a.ntiles) {
+        // The tile's last QK^T has retired (q_free completes together with this s_full): hand the NEXT tile's Q to the tensor
+        // pipe now, before this block's softmax - its first QK^T then run under this tile's last softmax / P.V / epilogue
+        // (written after the last P hand-over, the next tile's first S arrived ~2400 cycles later: event trace).
+        mbar_wait(&bars->q_free, nt & 1);
+        tc_fence_after();
+        write_q();
+      }
       uint32_t s[32], lo[32];
       tmem_ld_32x32(sp, s);
       tmem_wait_ld();
@@ -379,11 +427,6 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
       if (iloc >= 1) fold_o(i - 1, corr_prev);
       corr_prev = corr;
     }
-    if (t + t_stride < a.ntiles) {                   // hand the next tile's Q to the tensor pipe BEFORE this tile's last fold and
-      mbar_wait(&bars->q_free, nt & 1);              // epilogue: its first QK^T / softmax overlap them (all QK^T of this tile retired)
-      tc_fence_after();
-      write_q();
-    }
     fold_o(it - 1, corr_prev);
 
     // total row sum = sum of the two warpgroups' partial sums (buffer alternates per tile: one barrier suffices)
@@ -391,7 +434,22 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
     xl[g * 128 + trow] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float inv = 1.f / (l_run + xl[(g ^ 1) * 128 + trow]);
-    if (row_ok) {
+    if constexpr (STAGED) {
+#pragma unroll
+      for (int c = 0; c < HD / 4; ++c)
+        *reinterpret_cast<float4*>(ost + lane * HD + ((c ^ (lane & (LPR - 1))) * 4)) =
+            make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      __syncwarp();
+      const int r_in = lane / LPR, ch = lane % LPR;
+#pragma unroll
+      for (int k = 0; k < LPR; ++k) {
+        const int row = k * RPI + r_in, orow_g = grow - lane + row;          // global query row of staging row `row`
+        if (orow_g < a.nq)
+          *reinterpret_cast<float4*>(a.out + (int64_t)b * a.strideo + (int64_t)orow_g * a.ldo + h * DH + g * HD + ch * 4) =
+              *reinterpret_cast<const float4*>(ost + row * HD + ((ch ^ (row & (LPR - 1))) * 4));
+      }
+      __syncwarp();
+    } else if (row_ok) {
       float* orow = a.out + (int64_t)b * a.strideo + (int64_t)grow * a.ldo + h * DH + g * HD;
 #pragma unroll
       for (int c = 0; c < HD; c += 4)
