@@ -202,6 +202,33 @@ int og_match_fwd(const float* scores, int batch, int n, int m, float threshold,
                  int64_t* matches0, float* mscores0, int64_t* matches1, float* mscores1,
                  void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ground-truth match generation: the step immediately BEFORE the matching core in the reference's
+ * training / validation step (models/matching_module.py:84-93).  Replaces
+ * generate_gt_matches (models/gt_matches_generation.py:17-93) with reproject_keypoints /
+ * get_inverse_transformation (utils/misc.py:21-103): reprojection of both keypoint sets, the two
+ * N x M torch.cdist + min, the mutual check and the UNMATCHED (-1) / IGNORE (-2) marks.  The
+ * reference's threshold refinements (:56-67, :76-78) assign through boolean-mask copies and have
+ * no effect; they are not reproduced, so the thresholds are not parameters here.
+ * ------------------------------------------------------------------------------------------- */
+enum { OG_GT_PERSPECTIVE = 0, OG_GT_3D_REPROJECTION = 1 };   /* transformation['type'] (utils/misc.py:23-34) */
+typedef struct og_gt_transform {
+  int32_t type;
+  const float* H;                    /* perspective: [B,3,3]                                            */
+  const float* K0; const float* K1;  /* 3d: intrinsics [B,3,3]                                          */
+  const float* R;  const float* T;   /* 3d: relative pose [B,3,3], [B,3]  (x1 = R x0 + T)               */
+  const float* depth0;               /* 3d: per-keypoint depth [B,n] / [B,m], or depth images           */
+  const float* depth1;               /*     [B,depth{0,1}_h,depth{0,1}_w] when depth_is_image           */
+  int32_t depth_is_image;
+  int32_t depth0_h, depth0_w, depth1_h, depth1_w;
+} og_gt_transform;
+
+int64_t og_gt_matches_workspace_bytes(int batch, int n, int m);
+/* kpts0 [B,n,2], kpts1 [B,m,2] pixel coordinates; gt_matches0 [B,n], gt_matches1 [B,m] int64
+ * (index of the match, -1 unmatched, -2 ignore).  All pointers are device memory.                  */
+int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, int m, const og_gt_transform* tf,
+                      int64_t* gt_matches0, int64_t* gt_matches1, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,10 @@
 Public surface mirrors the reference for this one path:
     SuperGlue(config).forward(data)  -> {'context_descriptors0', 'context_descriptors1', 'scores'}
     MatchingCore(superglue)(data)    -> {'matches0', 'matching_scores0', 'matches1', 'matching_scores1'}
+and, for the step right before it in the reference's training / validation step:
+    generate_gt_matches(data, features0, features1, positive_threshold, negative_threshold) -> (data, y_true)
 """
+from .gt_matches import generate_gt_matches  # noqa: F401
 from .superglue import MatchingCore, PendingMatches, SuperGlue  # noqa: F401
 
 __version__ = '0.1.0'

@@ -44,6 +44,14 @@ class OgLinearArgs(C.Structure):
 # every symbol include/openglue_b200.h declares: (restype, argtypes)
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _CFG = C.POINTER(OgConfig)
+class OgGtTransform(C.Structure):       # include/openglue_b200.h: og_gt_transform
+    _fields_ = [('type', C.c_int32), ('H', C.c_void_p), ('K0', C.c_void_p), ('K1', C.c_void_p), ('R', C.c_void_p),
+                ('T', C.c_void_p), ('depth0', C.c_void_p), ('depth1', C.c_void_p), ('depth_is_image', C.c_int32),
+                ('depth0_h', C.c_int32), ('depth0_w', C.c_int32), ('depth1_h', C.c_int32), ('depth1_w', C.c_int32)]
+
+
+OG_GT_PERSPECTIVE, OG_GT_3D_REPROJECTION = 0, 1
+
 SYMBOLS = {
     'og_version': (_I, []),
     'og_last_error': (C.c_char_p, []),
@@ -64,6 +72,8 @@ SYMBOLS = {
     'og_sinkhorn_fwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _L, _P]),
     'og_match_workspace_bytes': (_L, [_I, _I, _I]),
     'og_match_fwd': (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
+    'og_gt_matches_workspace_bytes': (_L, [_I, _I, _I]),
+    'og_gt_matches_fwd': (_I, [_P, _P, _I, _I, _I, C.POINTER(OgGtTransform), _P, _P, _P, _L, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

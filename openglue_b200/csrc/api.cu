@@ -8,6 +8,7 @@
 #include "attention_tc.cuh"
 #include "sinkhorn.cuh"
 #include "match.cuh"
+#include "gt_matches.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -304,6 +305,26 @@ int og_match_fwd(const float* scores, int batch, int n, int m, float threshold, 
   OG_CHECK_ARG(batch > 0 && n > 0 && m > 0, "match: bad sizes");
   return match_launch(scores, batch, n, m, threshold, matches0, mscores0, matches1, mscores1, workspace,
                       workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t og_gt_matches_workspace_bytes(int batch, int n, int m) {
+  if (batch <= 0 || n <= 0 || m <= 0) return -1;
+  return gt_matches_workspace_bytes(batch, n, m);
+}
+
+int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, int m, const og_gt_transform* tf,
+                      int64_t* gt_matches0, int64_t* gt_matches1, void* workspace, int64_t workspace_bytes, void* stream) {
+  OG_CHECK_ARG(kpts0 && kpts1 && tf && gt_matches0 && gt_matches1 && workspace, "gt_matches: null pointer");
+  OG_CHECK_ARG(batch > 0 && n > 0 && m > 0, "gt_matches: bad sizes (the reference returns (None, None) for an empty keypoint set)");
+  OG_CHECK_ARG(tf->type == OG_GT_PERSPECTIVE || tf->type == OG_GT_3D_REPROJECTION, "gt_matches: unknown transformation type %d", tf->type);
+  if (tf->type == OG_GT_PERSPECTIVE) {
+    OG_CHECK_ARG(tf->H, "gt_matches: perspective transformation needs H");
+  } else {
+    OG_CHECK_ARG(tf->K0 && tf->K1 && tf->R && tf->T && tf->depth0 && tf->depth1, "gt_matches: 3d_reprojection needs K0, K1, R, T, depth0, depth1");
+    OG_CHECK_ARG(!tf->depth_is_image || (tf->depth0_h > 0 && tf->depth0_w > 0 && tf->depth1_h > 0 && tf->depth1_w > 0),
+                 "gt_matches: depth image sizes");
+  }
+  return gt_matches_launch(kpts0, kpts1, batch, n, m, *tf, gt_matches0, gt_matches1, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, int B, int n, int m,

@@ -148,3 +148,78 @@ def synthetic_pairs(batch: int, n: int, m: int, descriptor_dim: int, side_info_s
         'local_descriptors0': d0 * scale, 'local_descriptors1': d1 * scale,
         'image0_size': (w, h), 'image1_size': (w, h), 'planted_matches0': planted,
     }
+
+
+def synthetic_gt_scene(batch: int, n: int, m: int, kind: str = 'perspective', seed: int = 0, depth_image: bool = False,
+                       width: int = 640, height: int = 480, planted: float = 0.6, noise: float = 0.4,
+                       missing_depth: float = 0.1) -> dict:
+    """Two keypoint sets related by a known transformation, in the layout ``generate_gt_matches`` consumes
+    (reference models/gt_matches_generation.py:17-36: ``data['transformation']`` as collated by the datasets,
+    ``features{0,1}['keypoints']`` [B, n, 2] in pixels).  A fraction ``planted`` of image-1 keypoints are noisy
+    reprojections of image-0 keypoints; the rest are uniform.  kind: 'perspective' | '3d_reprojection'
+    (per-keypoint depth [B, n], or depth images [B, height, width] when ``depth_image``)."""
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda *s: torch.rand(*s, generator=g)
+    size = torch.tensor([width - 1.0, height - 1.0])
+    k0 = rnd(batch, n, 2) * (size - 8.0) + 4.0
+    n_pl = min(int(planted * m), n)
+    tf = {'type': [kind] * batch}
+    if kind == 'perspective':
+        H = torch.eye(3).repeat(batch, 1, 1)
+        H[:, :2, :2] += (rnd(batch, 2, 2) - 0.5) * 0.08
+        H[:, :2, 2] += (rnd(batch, 2) - 0.5) * 30.0
+        H[:, 2, :2] += (rnd(batch, 2) - 0.5) * 4e-5
+        tf['H'] = H
+        hom = torch.cat([k0, torch.ones(batch, n, 1)], 2) @ H.transpose(1, 2)
+        proj = hom[..., :2] / hom[..., 2:3]
+        z1_of_0 = None
+    elif kind == '3d_reprojection':
+        f0, f1 = 500.0 + 100.0 * rnd(batch), 520.0 + 100.0 * rnd(batch)
+        K0, K1 = torch.zeros(batch, 3, 3), torch.zeros(batch, 3, 3)
+        for K, f in ((K0, f0), (K1, f1)):
+            K[:, 0, 0] = f; K[:, 1, 1] = f * 1.01; K[:, 0, 2] = width / 2; K[:, 1, 2] = height / 2; K[:, 2, 2] = 1.0
+        ang = (rnd(batch, 3) - 0.5) * 0.12
+        R = torch.linalg.matrix_exp(torch.stack([torch.stack([torch.zeros(batch), -ang[:, 2], ang[:, 1]], 1),
+                                                 torch.stack([ang[:, 2], torch.zeros(batch), -ang[:, 0]], 1),
+                                                 torch.stack([-ang[:, 1], ang[:, 0], torch.zeros(batch)], 1)], 1))
+        T = (rnd(batch, 3) - 0.5) * torch.tensor([0.6, 0.4, 0.2]) + torch.tensor([0.0, 0.0, 0.15])
+        if depth_image:
+            yy, xx = torch.meshgrid(torch.arange(height).float(), torch.arange(width).float(), indexing='ij')
+            base = 4.0 + 1.5 * torch.sin(xx / 90.0)[None] + 1.0 * torch.cos(yy / 70.0)[None] + rnd(batch, 1, 1)
+            d0_img = base.clone()
+            d0_img[rnd(batch, height, width) < missing_depth] = 0.0
+            idx = k0.long()
+            z0 = d0_img[torch.arange(batch)[:, None], idx[..., 1], idx[..., 0]]
+        else:
+            z0 = 2.0 + 6.0 * rnd(batch, n)
+            z0[rnd(batch, n) < missing_depth] = 0.0
+        rays = torch.cat([k0, torch.ones(batch, n, 1)], 2) @ torch.linalg.inv(K0).transpose(1, 2)
+        X1 = (rays * torch.where(z0 > 0, z0, torch.ones_like(z0)).unsqueeze(-1)) @ R.transpose(1, 2) + T[:, None]
+        p = X1 @ K1.transpose(1, 2)
+        proj = p[..., :2] / p[..., 2:3]
+        z1_of_0 = X1[..., 2]
+        tf.update(K0=K0, K1=K1, R=R, T=T)
+    else:
+        raise ValueError(kind)
+    k1 = rnd(batch, m, 2) * (size - 8.0) + 4.0
+    perm = torch.stack([torch.randperm(n, generator=g)[:n_pl] for _ in range(batch)])
+    slot = torch.stack([torch.randperm(m, generator=g)[:n_pl] for _ in range(batch)])
+    bi = torch.arange(batch)[:, None]
+    planted_xy = proj[bi, perm] + noise * torch.randn(batch, n_pl, 2, generator=g)
+    inside = ((planted_xy > 2.0) & (planted_xy < size - 2.0)).all(-1)
+    k1[bi, slot] = torch.where(inside.unsqueeze(-1), planted_xy, k1[bi, slot])
+    if kind == '3d_reprojection':
+        if depth_image:
+            d1_img = 3.0 + 2.0 * rnd(batch, height, width)
+            d1_img[rnd(batch, height, width) < missing_depth] = 0.0
+            idx1 = k1.long()
+            zz = torch.where(inside, z1_of_0[bi, perm], d1_img[bi, idx1[bi, slot][..., 1], idx1[bi, slot][..., 0]])
+            d1_img[bi, idx1[bi, slot][..., 1], idx1[bi, slot][..., 0]] = zz     # consistent depth under the planted points
+            tf['depth0'], tf['depth1'] = d0_img, d1_img
+        else:
+            z1 = 2.0 + 6.0 * rnd(batch, m)
+            z1[bi, slot] = torch.where(inside, z1_of_0[bi, perm], z1[bi, slot])
+            z1[rnd(batch, m) < missing_depth] = 0.0
+            tf['depth0'], tf['depth1'] = z0, z1
+    return {'keypoints0': k0.contiguous(), 'keypoints1': k1.contiguous(), 'transformation': tf}
+
