@@ -108,6 +108,8 @@ class SuperGlue(nn.Module):
 
     def load_state_dict(self, *args, **kwargs):
         self._packed = None
+        self._tensors = None
+        self._epoch = getattr(self, '_epoch', 0) + 1
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode: bool = True):
@@ -115,8 +117,20 @@ class SuperGlue(nn.Module):
             self._packed = None
         return super().train(mode)
 
+    def _apply(self, fn, *args, **kwargs):               # .to() / .cuda() / .float(): storages move, the packed copy is stale
+        self._packed = None
+        self._tensors = None
+        self._epoch = getattr(self, '_epoch', 0) + 1
+        return super()._apply(fn, *args, **kwargs)
+
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        """Cheap fingerprint of the 333 parameter / buffer tensors (runs on every forward): in-place updates bump a tensor's
+        ``_version`` (monotonic, so the sum changes), moves go through ``_apply`` / ``load_state_dict``; the first and last
+        storages guard against ``.data`` reassignment."""
+        ts = getattr(self, '_tensors', None)
+        if ts is None:
+            ts = self._tensors = list(self.parameters()) + list(self.buffers())
+        return (getattr(self, '_epoch', 0), sum(t._version for t in ts), ts[0].data_ptr(), ts[-1].data_ptr())
 
     def packed_weights(self, device: torch.device) -> torch.Tensor:
         """Folded + packed weights on ``device`` (cached; rebuilt when a parameter changes)."""
