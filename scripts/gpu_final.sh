@@ -20,5 +20,3 @@ for n in ('bench','bench_ref','bench_C1','bench_C2','bench_C5'):
     except Exception as e:
         print(n, 'failed', e); print(open(f'gpurun_out/{n}.err').read()[-500:])
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 1 -c 1 -o gpurun_out/prof_attn6 -f python scripts/prof_ops.py attn 2 > gpurun_out/prof_attn.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_v8.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --cuda-graph 0 > gpurun_out/ncu_bench.log 2>&1
