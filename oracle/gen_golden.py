@@ -78,7 +78,15 @@ CASES = {
     # BASELINE.json configs[0] (the reference's CPU-runnable case): outputs stored sub-sampled
     'C1_planted':     (1, 512, 512, dict(descriptor_dim=256, num_stages=9, num_iters=20), 'planted', False),
     'C1_flat':        (1, 512, 512, dict(descriptor_dim=256, num_stages=9, num_iters=20), 'flat', False),
+    # BASELINE.json configs[1], [2] (headline), [4] at full depth and full batch: exactly the tensors bench.py times on rank 0
+    # (synthetic_pairs(batch, ..., seed=1234)).  matches0 / matching_scores0 for EVERY pair of the batch (the reference's
+    # MatchingTrainingModule.forward in fp32); log-scores (fp32 and fp64 reference runs) for the first SCORED_PAIRS pairs.
+    'C2_planted':     (32, 1024, 1024, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'planted', False),
+    'C3_planted':     (16, 2048, 2048, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'planted', False),
+    'C3_flat':        (1, 2048, 2048, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'flat', False),
+    'C5_planted':     (1, 4096, 1024, dict(descriptor_dim=128, num_stages=18, num_iters=50, side_info_size=6), 'planted', False),
 }
+SCORED_PAIRS = 2               # pairs of a big batch whose log-scores are stored (sub-sampled)
 MATCH_THRESHOLD = 0.2          # reference config/config.yaml:40
 
 
@@ -90,12 +98,14 @@ def run_reference(name):
     data = synthetic_pairs(batch, n, m, cfg['descriptor_dim'], cfg['positional_encoding']['side_info_size'],
                            family=family, seed=1234)
     out = {}
+    scored = min(batch, SCORED_PAIRS)
+    data_scored = {k: (v[:scored] if torch.is_tensor(v) else v) for k, v in data.items()}
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
         model = SuperGlue(copy.deepcopy(cfg)).eval()
         missing = model.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
         model = model.to(dtype)
-        d = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()}
+        d = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data_scored.items()}
         with torch.no_grad():
             res = model(d)
         out[tag] = {k: v.clone() for k, v in res.items()}
@@ -127,7 +137,7 @@ def run_reference(name):
     matches0, mscores0 = pred['matches0'], pred['matching_scores0']
 
     fx = {'name': name, 'config': cfg, 'weights_seed': 0, 'inputs_seed': 1234, 'family': family,
-          'batch': batch, 'n': n, 'm': m, 'match_threshold': MATCH_THRESHOLD,
+          'batch': batch, 'n': n, 'm': m, 'match_threshold': MATCH_THRESHOLD, 'scored_pairs': scored,
           'matches0': matches0, 'matching_scores0': mscores0,
           'ref32_vs_ref64_max_abs': float((out['f32']['scores'].double() - out['f64']['scores']).abs().max())}
     if full:
@@ -141,8 +151,10 @@ def run_reference(name):
     else:
         # big case: inputs/weights are regenerated from the seeds; keep a strided sample + checksums
         s32, s64 = out['f32']['scores'], out['f64']['scores']
-        fx['scores_f32_sample'] = s32[:, ::7, ::5].clone()
-        fx['scores_f64_sample'] = s64[:, ::7, ::5].clone()
+        sr, sc = (7, 5) if n <= 512 else (11, 13)
+        fx['sample_stride'] = (sr, sc)
+        fx['scores_f32_sample'] = s32[:, ::sr, ::sc].clone()
+        fx['scores_f64_sample'] = s64[:, ::sr, ::sc].clone()
         fx['scores_f32_lastrow'] = s32[:, -1, :].clone()
         fx['scores_f32_lastcol'] = s32[:, :, -1].clone()
         fx['scores_f64_rowsum'] = s64.sum(2)
@@ -152,6 +164,10 @@ def run_reference(name):
         fx['row_argmax_f64'] = s64[:, :-1, :-1].argmax(2)
         top2 = s64[:, :-1, :-1].topk(2, dim=2).values
         fx['row_top2_gap_f64'] = (top2[..., 0] - top2[..., 1]).float()
+        fx['col_argmax_f64'] = s64[:, :-1, :-1].argmax(1)
+        top2c = s64[:, :-1, :-1].topk(2, dim=1).values
+        fx['col_top2_gap_f64'] = (top2c[:, 0] - top2c[:, 1]).float()
+        fx['matching_scores0_f64'] = s64[:, :-1, :-1].max(2).values.exp().float()      # before the mutual mask
     return fx
 
 

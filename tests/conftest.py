@@ -32,6 +32,8 @@ def load_golden(name):
 
 GOLDEN_FULL = ['tiny_flat', 'tiny_planted', 'tiny_offset_s6', 'small_planted']
 GOLDEN_SAMPLED = ['C1_planted', 'C1_flat']
+# BASELINE.json configs[1], [2] (headline), [4] at full depth and at the batch bench.py times (oracle/gen_golden.py)
+GOLDEN_BIG = ['C2_planted', 'C3_planted', 'C3_flat', 'C5_planted']
 
 
 @pytest.fixture(scope='session')

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import superglue_oracle as O
-from conftest import GOLDEN_FULL, GOLDEN_SAMPLED
+from conftest import GOLDEN_BIG, GOLDEN_FULL, GOLDEN_SAMPLED
 
 
 @pytest.mark.parametrize('name', GOLDEN_FULL)
@@ -36,6 +36,31 @@ def test_oracle_matches_reference_c1(golden, name):
     assert (out['matching_scores0'] - fx['matching_scores0']).abs().max() <= 5e-6
     rel = (s.double().sum(2) - fx['scores_f64_rowsum']).abs().max() / fx['scores_f64_rowsum'].abs().max()
     assert rel < 1e-6
+
+
+@pytest.mark.parametrize('name', GOLDEN_BIG)
+def test_oracle_matches_reference_big(golden, name):
+    """BASELINE.json configs[1], [2], [4] at full depth: the oracle on the fixture's scored pairs (the first two of the
+    batch bench.py times) against the reference's fp32 run of the same pairs."""
+    fx = golden(name)
+    k = fx['scored_pairs']
+    data = {key: (v[:k] if torch.is_tensor(v) else v) for key, v in fx['data'].items()}
+    out = O.run(fx['state_dict'], fx['config'], data, fx['match_threshold'])
+    s, (sr, sc) = out['scores'], fx['sample_stride']
+    # same ATen ops on the same B = k batch: rounding noise only (|scores| reaches ~80 on the planted inputs)
+    assert (s[:, ::sr, ::sc] - fx['scores_f32_sample']).abs().max() <= 2e-5
+    assert (s[:, -1, :] - fx['scores_f32_lastrow']).abs().max() <= 2e-5
+    assert (s[:, :, -1] - fx['scores_f32_lastcol']).abs().max() <= 2e-5
+    assert (out['context_descriptors0'][:, ::4, ::8] - fx['ctx0_f32_sample']).abs().max() <= 5e-5
+    # matches0 / matching_scores0 of the fixture come from the reference's MatchingTrainingModule.forward over the WHOLE batch
+    assert torch.equal(out['matches0'], fx['matches0'][:k])
+    assert (out['matching_scores0'] - fx['matching_scores0'][:k]).abs().max() <= 2e-5
+    rel = (s.double().sum(2) - fx['scores_f64_rowsum']).abs().max() / fx['scores_f64_rowsum'].abs().max()
+    assert rel < 2e-5                       # fp32 run against the fp64 reference (ref32-vs-ref64 is ~1e-4 absolute here)
+    if 'planted' in name:
+        planted = fx['data']['planted_matches0']
+        has = planted >= 0
+        assert (fx['matches0'][has] == planted[has]).float().mean() > 0.995
 
 
 def test_planted_matches_are_recovered(golden):
