@@ -57,6 +57,8 @@ typedef struct og_config {
   float   sinkhorn_reg;         /* otp.reg                                                         */
   float   match_threshold;      /* inference.match_threshold (config/config.yaml:40)               */
   int32_t precision;            /* og_precision                                                    */
+  int32_t no_descriptors;       /* config.get('no_descriptors'): the GNN starts from the positional encoding alone
+                                   (superglue.py:45-49); the residual mix still uses the raw descriptors (:59-62) */
 } og_config;
 
 int         og_version(void);

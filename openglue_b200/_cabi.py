@@ -24,7 +24,7 @@ class OgConfig(C.Structure):
     _fields_ = [('descriptor_dim', C.c_int32), ('num_heads', C.c_int32), ('num_layers', C.c_int32),
                 ('side_info_size', C.c_int32), ('num_hidden', C.c_int32), ('hidden', C.c_int32 * OG_MAX_HIDDEN),
                 ('sinkhorn_iters', C.c_int32), ('sinkhorn_reg', C.c_float), ('match_threshold', C.c_float),
-                ('precision', C.c_int32)]
+                ('precision', C.c_int32), ('no_descriptors', C.c_int32)]
 
 
 class OgLinearArgs(C.Structure):
@@ -124,4 +124,5 @@ def make_config(config: dict, match_threshold: float = 0.2, precision: int = OG_
     c.sinkhorn_reg = float(config['otp']['reg'])
     c.match_threshold = float(match_threshold)
     c.precision = int(precision)
+    c.no_descriptors = int(bool(config.get('no_descriptors', False)))
     return c

@@ -376,10 +376,10 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi
         cur = bufs[i & 1];
       } else {                        // last layer: + local descriptors, per image (separate user tensors)
         og_linear_args a = lin(cur, kin, kin, Wp + L.kenc_w[i], Wp + L.kenc_b[i], R0, kout, x0, d);
-        a.R = desc0; a.ldr = d;
+        if (!cfg->no_descriptors) { a.R = desc0; a.ldr = d; }          // superglue.py:45-55
         if ((rc = linear_dispatch(a, OG_PREC_FP32, st)) != OG_OK) return rc;
         og_linear_args b = lin(cur + (int64_t)R0 * kin, kin, kin, Wp + L.kenc_w[i], Wp + L.kenc_b[i], R1, kout, x1, d);
-        b.R = desc1; b.ldr = d;
+        if (!cfg->no_descriptors) { b.R = desc1; b.ldr = d; }
         if ((rc = linear_dispatch(b, OG_PREC_FP32, st)) != OG_OK) return rc;
       }
     }

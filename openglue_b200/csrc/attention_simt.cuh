@@ -137,11 +137,10 @@ inline int attention_simt_launch(const AttnArgs& a, int head_dim, cudaStream_t s
 #define OG_ATTN_CASE(DH_)                                                                        \
   case DH_: {                                                                                    \
     constexpr int smem = (DH_ * (ATQ + ATK) + ATK * DH_ + ATK * ATQ) * (int)sizeof(float);       \
-    static bool attr_set = false;                                                                \
-    if (!attr_set) {                                                                             \
+    static DeviceFlags attr_set;                                                                \
+    if (attr_set.once()) {                                                                             \
       OG_CUDA(cudaFuncSetAttribute(attention_simt_kernel<DH_>,                                   \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
-      attr_set = true;                                                                           \
     }                                                                                            \
     attention_simt_kernel<DH_><<<grid, 256, smem, stream>>>(a);                                  \
   } break;

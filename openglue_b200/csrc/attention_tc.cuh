@@ -474,10 +474,9 @@ inline int attention_tc_launch_t(const TcAttnArgs& a, const float* khi, const fl
   if ((rc = tc::make_tmap_2d(&mkl, klo, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK / CG)) != OG_OK) return rc;
   if ((rc = tc::make_tmap_2d(&mvh, vthi, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
   if ((rc = tc::make_tmap_2d(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceFlags attr_set;
+  if (attr_set.once()) {
     OG_CUDA(cudaFuncSetAttribute(attention_tc_kernel<DH, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<DH, CG>()));
-    attr_set = true;
   }
   TcAttnArgs ap = a;
   ap.nqg = cdiv(cdiv(a.nq, BM), CG);                                             // CG = 2: an odd last query block gets a phantom partner

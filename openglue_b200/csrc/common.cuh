@@ -22,19 +22,32 @@ inline int fail(int code, const char* fmt, ...) {
 
 inline int& launch_counter() { static thread_local int c = 0; return c; }
 
-struct DeviceInfo { int sm_count = 0, cc_major = 0, cc_minor = 0; bool ok = false; };
+// Per-device state (a process may drive several GPUs: MatchingCore(device=...), .to(dev)): the capability cache and the
+// "function attribute already set" flags are indexed by the CURRENT device, never process-global.
+constexpr int OG_MAX_DEVICES = 64;
+inline int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= OG_MAX_DEVICES) dev = 0; return dev; }
+
+struct DeviceInfo { int sm_count = 0, cc_major = 0, cc_minor = 0; bool ok = false, probed = false; };
 inline const DeviceInfo& device_info() {
-  // immutable per-process capability cache (first use wins; one device per process by design)
-  static DeviceInfo info = [] {
-    DeviceInfo d; int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return d;
+  static DeviceInfo info[OG_MAX_DEVICES];          // immutable once probed (a benign race writes identical values)
+  const int dev = current_device();
+  DeviceInfo& d = info[dev];
+  if (!d.probed) {
+    DeviceInfo t; t.probed = true;
+    int real = 0;
     cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return d;
-    d.sm_count = p.multiProcessorCount; d.cc_major = p.major; d.cc_minor = p.minor; d.ok = true;
-    return d;
-  }();
-  return info;
+    if (cudaGetDevice(&real) == cudaSuccess && cudaGetDeviceProperties(&p, real) == cudaSuccess) {
+      t.sm_count = p.multiProcessorCount; t.cc_major = p.major; t.cc_minor = p.minor; t.ok = true;
+    }
+    d = t;
+  }
+  return d;
 }
+// One flag per device for "cudaFuncSetAttribute done": declare `static DeviceFlags f;` next to the launch and test f.once().
+struct DeviceFlags {
+  bool set[OG_MAX_DEVICES] = {};
+  bool once() { const int dev = current_device(); if (set[dev]) return false; set[dev] = true; return true; }
+};
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

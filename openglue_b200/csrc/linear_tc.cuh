@@ -265,10 +265,9 @@ inline int linear_tc_launch_mode(const TcLinearArgs& a, const float* Bhi, const 
   if (rc != OG_OK) return rc;
   rc = tc::make_tmap_2d(&mlo, Blo, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, BN);
   if (rc != OG_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceFlags attr_set;
+  if (attr_set.once()) {
     OG_CUDA(cudaFuncSetAttribute(linear_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(MODE)));
-    attr_set = true;
   }
   dim3 grid(cdiv(a.nout, BN), cdiv(a.rows, BM), a.batch);
   linear_tc_kernel<MODE><<<grid, THREADS, smem_bytes(MODE), stream>>>(mhi, mlo, a);

@@ -452,10 +452,9 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
                         TcLinearArgs, Sched, int);
   static const Kern kerns[5] = {linear_tc2_kernel<PAIR, 0, 0>, linear_tc2_kernel<PAIR, 0, 1>, linear_tc2_kernel<PAIR, 0, 2>,
                                 linear_tc2_kernel<PAIR, 0, 3>, linear_tc2_kernel<PAIR, 1, 1>};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceFlags attr_set;
+  if (attr_set.once()) {
     for (Kern k : kerns) OG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
   }
   const Kern kern = r_tma ? kerns[4] : kerns[outk];
   Sched sc;

@@ -309,12 +309,11 @@ inline int64_t sinkhorn_workspace_bytes(int B, int n, int m) {
 
 template <int V>
 inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {                       // largest request of this instantiation: m = 128 V  =>  mpad = 128 V + 4
+  static DeviceFlags attr_set;
+  if (attr_set.once()) {                       // largest request of this instantiation: m = 128 V  =>  mpad = 128 V + 4
     OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(((1 + SINK_WARPS) * (128 * V + 4) + SINK_WARPS * SINK_SLOTS * 128 * V) * sizeof(float) +
                                        SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128)));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.B * a.SP);

@@ -29,8 +29,10 @@ def shard_pairs(data: Dict[str, object], rank: int, world_size: int) -> Dict[str
 def match_statistics(matches0: torch.Tensor, matching_scores0: torch.Tensor) -> torch.Tensor:
     """[#pairs, #matches, sum of match confidences] of a shard (float64, on the tensors' device)."""
     ok = matches0 >= 0
-    return torch.stack([torch.tensor(float(matches0.shape[0]), device=matches0.device, dtype=torch.float64),
-                        ok.sum().double(), matching_scores0.double()[ok].sum()])
+    # no boolean-mask indexing, no host scalars moved to the device: nothing here synchronises with the host
+    conf = torch.where(ok, matching_scores0.double(), matching_scores0.new_zeros((), dtype=torch.float64)).sum()
+    pairs = torch.full((), float(matches0.shape[0]), device=matches0.device, dtype=torch.float64)
+    return torch.stack([pairs, ok.sum().double(), conf])
 
 
 def all_reduce_statistics(stats: torch.Tensor, group=None) -> Dict[str, float]:

@@ -72,8 +72,6 @@ class SuperGlue(nn.Module):
             raise ValueError(f"Attention type {gnn['attention']} is not supported (only 'softmax').")
         if gnn.get('embed_dim', d) != d or pe.get('output_size', d) != d:
             raise ValueError('embed_dim / positional_encoding.output_size must equal descriptor_dim')
-        if config.get('no_descriptors', False):
-            raise ValueError('no_descriptors=True is not supported by openglue_b200')
         hidden = list(pe.get('hidden_layers_sizes') or [])
         self.positional_encoding = _Holder()
         self.positional_encoding.encoder = _feed_forward_params(pe.get('side_info_size', 1) + 2, *hidden, d)
@@ -103,6 +101,11 @@ class SuperGlue(nn.Module):
     def og_config(self) -> _cabi.OgConfig:
         return _cabi.make_config(self.config, self.config.get('match_threshold', 0.2), self._precision())
 
+    def _bump_alloc(self) -> None:
+        """Device buffers whose addresses a captured CUDA graph bakes in (workspace, packed weights and their operand
+        splits) were reallocated: graphs captured against the old addresses must not be replayed."""
+        self._alloc_gen = getattr(self, '_alloc_gen', 0) + 1
+
     def invalidate_packed(self) -> None:
         self._packed = None
 
@@ -124,13 +127,17 @@ class SuperGlue(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def _weights_version(self):
-        """Cheap fingerprint of the 333 parameter / buffer tensors (runs on every forward): in-place updates bump a tensor's
-        ``_version`` (monotonic, so the sum changes), moves go through ``_apply`` / ``load_state_dict``; the first and last
-        storages guard against ``.data`` reassignment."""
+        """Cheap fingerprint of the 333 parameter / buffer tensors (runs on every forward, ~50 us): in-place updates bump a
+        tensor's ``_version`` (monotonic, so the sum changes), moves go through ``_apply`` / ``load_state_dict``, and the
+        storage addresses of ALL tensors catch ``p.data = new`` / ``vector_to_parameters`` / EMA swaps on any of them."""
         ts = getattr(self, '_tensors', None)
         if ts is None:
             ts = self._tensors = list(self.parameters()) + list(self.buffers())
-        return (getattr(self, '_epoch', 0), sum(t._version for t in ts), ts[0].data_ptr(), ts[-1].data_ptr())
+        ver = ptr = 0
+        for i, t in enumerate(ts):
+            ver += t._version
+            ptr ^= t.data_ptr() * (2 * i + 1)
+        return (getattr(self, '_epoch', 0), ver, ptr & 0xFFFFFFFFFFFFFFFF)
 
     def packed_weights(self, device: torch.device) -> torch.Tensor:
         """Folded + packed weights on ``device`` (cached; rebuilt when a parameter changes)."""
@@ -139,6 +146,7 @@ class SuperGlue(nn.Module):
             self._ogcfg = self.og_config()
             self._packed = pack_weights(self.state_dict(), self.config, self._ogcfg).to(device)
             self._packed_hi = self._packed_lo = None
+            self._bump_alloc()
             if self._precision() == _cabi.OG_PREC_TF32X3:      # operand split for the tcgen05 kernels
                 self._packed_hi, self._packed_lo = torch.empty_like(self._packed), torch.empty_like(self._packed)
                 with torch.cuda.device(device):
@@ -159,7 +167,8 @@ class SuperGlue(nn.Module):
         w, h = data[f'image{idx}_size'][:2]
         return float(w), float(h)
 
-    def run(self, data: dict, want_matches: bool, want_context: bool = True) -> Dict[str, torch.Tensor]:
+    def run(self, data: dict, want_matches: bool, want_context: bool = True,
+            match_threshold: Optional[float] = None) -> Dict[str, torch.Tensor]:
         if self.training:
             raise RuntimeError('openglue_b200.SuperGlue implements the eval-mode forward pass only '
                                '(train-mode BatchNorm statistics and backward are not built yet)')
@@ -194,11 +203,15 @@ class SuperGlue(nn.Module):
         with torch.cuda.device(dev):
             packed = self.packed_weights(dev)
             cfg = self._ogcfg
+            if match_threshold is not None and float(match_threshold) != cfg.match_threshold:
+                cfg = _cabi.OgConfig.from_buffer_copy(cfg)             # per call: never written back into the shared config
+                cfg.match_threshold = float(match_threshold)
             ws_bytes = lib.og_workspace_bytes(cfg, B, n, m)
             if ws_bytes < 0:
                 _cabi.check(int(ws_bytes), 'og_workspace_bytes')
             if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
                 self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                self._bump_alloc()
             scores = torch.empty(B, n + 1, m + 1, dtype=torch.float32, device=dev)
             out = {'scores': scores}
             ctx0 = ctx1 = None
@@ -253,11 +266,11 @@ class MatchingCore(nn.Module):
                  use_cuda_graph: bool = False):
         super().__init__()
         self.superglue = superglue
-        self.superglue.config['match_threshold'] = match_threshold
-        self.superglue.invalidate_packed()
+        self.match_threshold = float(match_threshold)           # per core; the shared SuperGlue's config is not touched
         self.device = torch.device(device) if device is not None else None
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, tuple] = {}
+        self.max_graphs = 4                                     # captured shapes kept (alternating shapes do not re-capture)
 
     _TENSOR_KEYS = ('keypoints0', 'keypoints1', 'side_info0', 'side_info1', 'local_descriptors0', 'local_descriptors1')
     _OUT_KEYS = ('matches0', 'matching_scores0', 'matches1', 'matching_scores1')
@@ -265,23 +278,29 @@ class MatchingCore(nn.Module):
     def _run_graph(self, data: dict, dev: torch.device) -> Dict[str, torch.Tensor]:
         """Replay (capturing on first use) the CUDA graph for this shape; inputs are copied into its static buffers."""
         shapes = tuple(tuple(data[k].shape) for k in self._TENSOR_KEYS)
-        sizes = (tuple(data['image0_size']) if 'image0_size' in data else tuple(data['image0'].shape[-2:]),
-                 tuple(data['image1_size']) if 'image1_size' in data else tuple(data['image1'].shape[-2:]))
-        key = (shapes, sizes, str(dev), self.superglue._weights_version())
+        sizes = (SuperGlue._image_wh(data, 0), SuperGlue._image_wh(data, 1))       # plain floats (collated sizes are tensors)
+        key = (shapes, sizes, str(dev), self.superglue._weights_version(), self.match_threshold)
         entry = self._graphs.get(key)
+        if entry is not None and entry[3] != getattr(self.superglue, '_alloc_gen', 0):
+            # the SuperGlue's workspace / packed weights were reallocated since this graph was captured (a bigger call
+            # on the same module, another core sharing it): its kernels would read and write freed blocks
+            del self._graphs[key]
+            entry = None
         if entry is None:
             static = dict(data)
             for k in self._TENSOR_KEYS:
                 static[k] = torch.empty(data[k].shape, dtype=torch.float32, device=dev)
                 static[k].copy_(data[k], non_blocking=True)
-            self.superglue.run(static, want_matches=True, want_context=False)        # warm-up: builds weights, workspace, attributes
+            run = lambda: self.superglue.run(static, want_matches=True, want_context=False, match_threshold=self.match_threshold)
+            run()                                                                    # warm-up: builds weights, workspace, attributes
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self.superglue.run(static, want_matches=True, want_context=False)
-            self._graphs = {key: (graph, static, out)}                               # one shape at a time: bounded memory
-            entry = self._graphs[key]
-        graph, static, out = entry
+                out = run()
+            while len(self._graphs) >= self.max_graphs:                              # bounded memory: drop the oldest shape
+                del self._graphs[next(iter(self._graphs))]
+            entry = self._graphs[key] = (graph, static, out, getattr(self.superglue, '_alloc_gen', 0))
+        graph, static, out, _ = entry
         for k in self._TENSOR_KEYS:
             static[k].copy_(data[k], non_blocking=True)
         graph.replay()
@@ -300,7 +319,7 @@ class MatchingCore(nn.Module):
                 data = dict(data)
                 for k in self._TENSOR_KEYS:
                     data[k] = data[k].to(dev, non_blocking=True)
-            out = self.superglue.run(data, want_matches=True, want_context=False)
+            out = self.superglue.run(data, want_matches=True, want_context=False, match_threshold=self.match_threshold)
         res = {k: out[k] for k in self._OUT_KEYS}
         if want_scores:
             res['scores'] = out['scores']
@@ -349,7 +368,7 @@ class MatchingCore(nn.Module):
             if self.use_cuda_graph:
                 out = self._run_graph(dev_data, dev)
             else:
-                out = self.superglue.run(dev_data, want_matches=True, want_context=False)
+                out = self.superglue.run(dev_data, want_matches=True, want_context=False, match_threshold=self.match_threshold)
             computed = torch.cuda.Event()
             computed.record(compute)
             pipe['free'][slot] = computed

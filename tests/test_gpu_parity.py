@@ -154,7 +154,9 @@ def test_forward_matches_reference_big(golden, name, precision, pair):
     assert e64 <= bound and e32 <= bound and edb <= bound and rel < 2e-5
     assert torch.equal(s[:, :-1, :-1].argmax(2)[fx['row_top2_gap_f64'] > 2 * bound], i0[fx['row_top2_gap_f64'] > 2 * bound])
     assert torch.equal(m0[:k][decisive], fx['matches0'][:k][decisive])
-    assert (ms0[:k][decisive] - fx['matching_scores0_f64'][decisive]).abs().max() <= TOL     # exp(max_j) of the fp64 reference
+    mutual = decisive & (fx['matching_scores0'][:k] > 0)                                  # non-mutual rows carry 0
+    assert (ms0[:k][mutual] - fx['matching_scores0_f64'][mutual]).abs().max() <= TOL     # exp(max_j) of the fp64 reference
+    assert (ms0[:k][decisive & ~mutual] == 0).all()
     if 'planted' in name:                                        # decisive inputs: identical on EVERY pair of the batch
         assert mism_all == 0
         assert ems <= bound

@@ -28,9 +28,9 @@ def test_library_exports_every_header_symbol():
 
 
 def test_abi_struct_sizes_match_header():
-    # og_config: 5 + 8 ints, int, float, float, int = 17 * 4 bytes
+    # og_config: 5 + 8 ints, int, float, float, int, int = 18 * 4 bytes
     import ctypes as C
-    assert C.sizeof(_cabi.OgConfig) == 17 * 4
+    assert C.sizeof(_cabi.OgConfig) == 18 * 4
     assert C.sizeof(_cabi.OgLinearArgs) == 192
 
 
