@@ -231,6 +231,17 @@ int64_t og_gt_matches_workspace_bytes(int batch, int n, int m);
 int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, int m, const og_gt_transform* tf,
                       int64_t* gt_matches0, int64_t* gt_matches1, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Matching loss: the step immediately AFTER the matching core in the reference's training step
+ * (models/matching_module.py:101).  Replaces criterion (utils/losses.py:7-53) for margin = None (every
+ * shipped config): loss[0] = 'loss' (negative log-likelihood of the ground-truth assignment, mean per set and
+ * per pair), loss[1] = 'metric_loss' = 0.  gt_matches0 [B,n] / gt_matches1 [B,m] int64 as og_gt_matches_fwd
+ * writes them (-1 unmatched, -2 ignore).  dscores (optional, [B,n+1,m+1], ZERO-FILLED by the caller) receives
+ * grad_scale * d loss / d scores (a sparse scatter: the backward pass of the gather).  Deterministic.      */
+int64_t og_criterion_workspace_bytes(int batch);
+int og_criterion_fwd(const float* scores, const int64_t* gt_matches0, const int64_t* gt_matches1, int batch, int n, int m,
+                     float* loss, float* dscores, float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

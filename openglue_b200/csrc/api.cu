@@ -9,6 +9,7 @@
 #include "sinkhorn.cuh"
 #include "match.cuh"
 #include "gt_matches.cuh"
+#include "criterion.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -325,6 +326,16 @@ int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, 
                  "gt_matches: depth image sizes");
   }
   return gt_matches_launch(kpts0, kpts1, batch, n, m, *tf, gt_matches0, gt_matches1, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t og_criterion_workspace_bytes(int batch) { return batch > 0 ? criterion_workspace_bytes(batch) : -1; }
+
+int og_criterion_fwd(const float* scores, const int64_t* gt_matches0, const int64_t* gt_matches1, int batch, int n, int m,
+                     float* loss, float* dscores, float grad_scale, void* workspace, int64_t workspace_bytes, void* stream) {
+  OG_CHECK_ARG(scores && gt_matches0 && gt_matches1 && loss && workspace, "criterion: null pointer");
+  OG_CHECK_ARG(batch > 0 && n > 0 && m > 0, "criterion: bad sizes");
+  return criterion_launch(scores, gt_matches0, gt_matches1, batch, n, m, loss, dscores, grad_scale, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
 }
 
 int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, int B, int n, int m,

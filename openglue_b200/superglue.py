@@ -306,23 +306,25 @@ class MatchingCore(nn.Module):
         graph.replay()
         return out
 
-    def forward(self, data: dict, want_scores: bool = False) -> Dict[str, torch.Tensor]:
+    def forward(self, data: dict, want_scores: bool = False, borrow: bool = False) -> Dict[str, torch.Tensor]:
+        """``borrow=True`` (device input, CUDA-graph mode): return the graph's own output buffers instead of copies; they are
+        overwritten by the next call on this core (use it when the results are consumed on the same stream right away)."""
         host = data['keypoints0'].device.type == 'cpu'
         dev = (self.device or torch.device('cuda', torch.cuda.current_device())) if host else data['keypoints0'].device
+        keys = self._OUT_KEYS + (('scores',) if want_scores else ())
         if self.use_cuda_graph:
             with torch.cuda.device(dev):
                 out = self._run_graph(data, dev)
-            if not host:                            # the graph's output buffers are overwritten by the next replay
-                out = {k: v.clone() for k, v in out.items()}
+            res = {k: out[k] for k in keys}
+            if not host and not borrow:             # the graph's output buffers are overwritten by the next replay
+                res = {k: v.clone() for k, v in res.items()}
         else:
             if host:
                 data = dict(data)
                 for k in self._TENSOR_KEYS:
                     data[k] = data[k].to(dev, non_blocking=True)
             out = self.superglue.run(data, want_matches=True, want_context=False, match_threshold=self.match_threshold)
-        res = {k: out[k] for k in self._OUT_KEYS}
-        if want_scores:
-            res['scores'] = out['scores']
+            res = {k: out[k] for k in keys}
         if host:
             res = {k: v.to('cpu', non_blocking=True) for k, v in res.items()}
             torch.cuda.current_stream(dev).synchronize()

@@ -83,6 +83,7 @@ CASES = {
     # MatchingTrainingModule.forward in fp32); log-scores (fp32 and fp64 reference runs) for the first SCORED_PAIRS pairs.
     'C2_planted':     (32, 1024, 1024, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'planted', False),
     'C3_planted':     (16, 2048, 2048, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'planted', False),
+    'C4_planted':     (32, 2048, 2048, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'planted', False),   # configs[3]: 32 pairs / GPU
     'C3_flat':        (1, 2048, 2048, dict(descriptor_dim=256, num_stages=9, num_iters=100), 'flat', False),
     'C5_planted':     (1, 4096, 1024, dict(descriptor_dim=128, num_stages=18, num_iters=50, side_info_size=6), 'planted', False),
 }

@@ -65,12 +65,35 @@ def _round_mantissa(x: Tensor, keep_bits: int) -> Tensor:
 class EmulatedContraction(Contraction):
     """Operand-rounding emulation of tensor-core arithmetic (fp32 accumulate).
 
-    mode per tag-prefix: 'fp32' | 'tf32' | 'tf32x3' | 'bf16' | 'bf16x3'.
+    mode per tag-prefix: 'fp32' | 'tf32' | 'tf32x3' | 'bf16' | 'bf16x3' | 'fp16x3' | 'fp16x3t'.
+    'fp16x3': both operands scaled by a per-tensor power of two so that a BOUND on max|x| lands in [2^14, 2^15)
+    (the bound is ``2**headroom`` times the true maximum: the kernels derive it from norms, not from the data),
+    split into hi = fp16(x), lo = fp16(x - hi) (IEEE half incl. subnormals: absolute floor 2^-25 after scaling),
+    three products with fp32 accumulation, un-scaled afterwards.  'fp16x3t': lo is TRUNCATED to fp16 instead of
+    rounded (what a cvt.rz / bit-mask split would do).
     ``modes`` maps a tag prefix ('proj', 'qk', 'pv', 'mlp', 'final', 'score',
     'kenc') to a mode; '*' is the default."""
 
-    def __init__(self, modes: Dict[str, str]):
+    def __init__(self, modes: Dict[str, str], headroom: int = 6):
         self.modes = modes
+        self.headroom = headroom
+
+    def _split_f16(self, x: Tensor, truncate_lo: bool = False):
+        amax = float(x.abs().max())
+        if amax == 0.0 or not math.isfinite(amax):
+            return x, torch.zeros_like(x), 1.0
+        e = 14 - self.headroom - math.floor(math.log2(amax))        # amax * 2^e in [2^(14-h), 2^(15-h))
+        sc = 2.0 ** e
+        xs = x * sc
+        hi = xs.half().float() if x.dtype == torch.float32 else xs.half().to(x.dtype)
+        r = xs - hi
+        if truncate_lo:
+            lo = r.half()
+            over = lo.to(r.dtype).abs() > r.abs()
+            lo = torch.where(over, torch.nextafter(lo, torch.zeros_like(lo)), lo).to(x.dtype)
+        else:
+            lo = r.half().to(x.dtype)
+        return hi, lo, sc
 
     def _mode(self, tag: str) -> str:
         for k, v in self.modes.items():
@@ -90,6 +113,10 @@ class EmulatedContraction(Contraction):
     def _mm(self, a: Tensor, b: Tensor, mode: str) -> Tensor:
         if mode == 'fp32':
             return torch.matmul(a, b)
+        if mode in ('fp16x3', 'fp16x3t'):
+            ah, al, sa = self._split_f16(a, mode == 'fp16x3t')
+            bh, bl, sb = self._split_f16(b, mode == 'fp16x3t')
+            return (torch.matmul(al, bh) + torch.matmul(ah, bl) + torch.matmul(ah, bh)) * (1.0 / (sa * sb))
         bits = 10 if mode.startswith('tf32') else 7
         if mode in ('tf32', 'bf16'):
             return torch.matmul(_round_mantissa(a, bits), _round_mantissa(b, bits))

@@ -1,5 +1,7 @@
-"""Run the three dominant kernels once each at the headline (C3) shapes - the target of
-`ncu --set full -k regex:...` captures.   python scripts/prof_ops.py [attn|linear|sinkhorn|all] [reps]"""
+"""Run the dominant kernels once each at the headline (C3) shapes - the target of
+`ncu --set full -k regex:...` captures.   python scripts/prof_ops.py [attn|xattn|qkv|linear|sinkhorn|all] [reps]
+(xattn = one cross-attention launch: 16 sequences, N x M; qkv = the three projection GEMM variants of one layer:
+Q -> fp32 Y, K -> split row-major, V -> split transposed)"""
 import ctypes as C
 import os
 import sys
@@ -35,6 +37,42 @@ if which in ('attn', 'all'):
     for _ in range(reps):
         _cabi.check(lib.og_attention_tc_fwd(p(q), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), n, p(o), d, n * d,
                                             nb, n, n, H, d // H, st), 'attn')
+if which in ('xattn', 'evidence'):
+    q = torch.randn(B * n, d, device=dev)
+    k = torch.randn(B * n, d, device=dev)
+    vt = torch.randn(B * d, n, device=dev)
+    khi, klo = split(k)
+    vthi, vtlo = split(vt)
+    o = torch.empty(B * n, d, device=dev)
+    for _ in range(reps):
+        _cabi.check(lib.og_attention_tc_fwd(p(q), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), n, p(o), d, n * d,
+                                            B, n, n, H, d // H, st), 'xattn')
+if which in ('qkv', 'evidence'):
+    rows = 2 * B * n
+    A = torch.randn(rows, d, device=dev)
+    W = torch.randn(d, d, device=dev) / 16
+    Whi, Wlo = split(W)
+    bias = torch.randn(d, device=dev)
+    Y = torch.empty(rows, d, device=dev)
+    Yhi, Ylo = torch.empty_like(Y), torch.empty_like(Y)
+    Yt_hi, Yt_lo = torch.empty(2 * B, d, n, device=dev), torch.empty(2 * B, d, n, device=dev)
+    for kind in ('q', 'k', 'v'):
+        a = _cabi.OgLinearArgs()
+        a.k1, a.k2, a.ldw, a.strideW = d, 0, d, 0
+        a.bias = bias.data_ptr()
+        a.nout, a.alpha, a.relu = d, 1.0, 0
+        if kind == 'v':                                  # per sequence: transposed split output [B, d, n]
+            a.A, a.lda, a.strideA = A.data_ptr(), d, n * d
+            a.rows, a.batch, a.ldyt, a.strideYt, a.ldy = n, 2 * B, n, d * n, d
+            outs = (None, None, p(Yt_hi), p(Yt_lo))
+        else:
+            a.A, a.lda, a.strideA = A.data_ptr(), d, 0
+            a.rows, a.batch, a.ldy, a.strideY = rows, 1, d, 0
+            if kind == 'q':
+                a.Y = Y.data_ptr()
+            outs = (None, None, None, None) if kind == 'q' else (p(Yhi), p(Ylo), None, None)
+        for _ in range(reps):
+            _cabi.check(lib.og_linear_tc_fwd(C.byref(a), p(Whi), p(Wlo), *outs, 2, st), 'qkv ' + kind)
 if which in ('linear', 'all'):
     rows = 2 * B * n
     for (k1, k2, nout, relu, resid) in ((256, 0, 256, 0, 0), (256, 256, 512, 1, 0), (512, 0, 256, 0, 1)):
