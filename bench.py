@@ -269,7 +269,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='C3', choices=sorted(BASELINE_CONFIGS))
     ap.add_argument('--pairs-per-gpu', type=int, default=None)
-    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'tf32x3'), choices=['fp32', 'tf32x3'])
+    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'tf32x3'), choices=['fp32', 'tf32x3', 'fp16x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true', help='skip the check of the timed output against tests/golden/<workload>_planted.pt')
     ap.add_argument('--cuda-graph', type=int, default=1, help='replay the launch schedule from a CUDA graph (default on)')
@@ -414,7 +414,7 @@ def main():
     nb = 2 * batch if n == m else batch
     qkv = torch.randn(nb * n, 3 * d, device=dev)
     o = torch.empty(nb * n, d, device=dev)
-    prec = {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3}[args.precision]
+    prec = {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3, 'fp16x3': _cabi.OG_PREC_FP16X3}[args.precision]
     p = lambda t, off=0: C.c_void_p(t.data_ptr() + off * 4)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -430,6 +430,24 @@ def main():
         def attn():
             _cabi.check(lib.og_attention_tc_fwd(p(qq), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), ldv, p(o), d, n * d,
                                                 nb, n, n, H, d // H, st), 'og_attention_tc_fwd')
+    elif args.precision == 'fp16x3':
+        def split16(x2d):
+            hi = torch.empty(x2d.shape, dtype=torch.float16, device=dev)
+            lo, meta = torch.empty_like(hi), torch.zeros(4, device=dev)
+            _cabi.check(lib.og_weight_split_f16(p(x2d), None, x2d.shape[0], x2d.shape[1], p(hi), p(lo), p(meta), st), 'og_weight_split_f16')
+            return hi, lo, meta
+        kk = torch.randn(nb * n, d, device=dev)
+        ldv = (n + 7) // 8 * 8
+        vt = torch.randn(nb * d, ldv, device=dev)
+        kh16, kl16, kmeta = split16(kk)
+        vh16, vl16, vmeta = split16(vt)
+        qq = torch.randn(nb * n, d, device=dev)
+        qamax = torch.zeros(1, device=dev)
+        _cabi.check(lib.og_amax(p(qq), qq.numel(), p(qamax), st), 'og_amax')
+
+        def attn():
+            _cabi.check(lib.og_attention_f16_fwd(p(qq), d, n * d, p(qamax), p(kh16), p(kl16), d, p(kmeta), p(vh16), p(vl16), ldv, p(vmeta),
+                                                 p(o), d, n * d, None, nb, n, n, H, d // H, 0, st), 'og_attention_f16_fwd')
     else:
         def attn():
             _cabi.check(lib.og_attention_fwd(p(qkv), 3 * d, n * 3 * d, p(qkv, d), 3 * d, n * 3 * d, p(qkv, 2 * d), 3 * d,
@@ -462,13 +480,15 @@ def main():
         return
     traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath) and args.workload == 'C3' and batch == 16 and args.precision == 'tf32x3':
+    if os.path.exists(tpath) and args.workload == 'C3' and batch == 16 and args.precision == 'tf32x3':     # (tf32 kernels only)
         traffic = json.load(open(tpath))     # ncu dram bytes per launch, captured at exactly these shapes
     fl = flops_per_pair(n, m, d, stages, s_dim)
     line = {
         'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'tf32x3 (fp32 accumulate)',
+        'vs_baseline': None,
+        'dtype': {'fp32': 'f32', 'tf32x3': 'tf32x3 (tf32 hi/lo operands, 3 products, fp32 accumulate)',
+                  'fp16x3': 'fp16x3 (fp16 hi/lo operands with power-of-two tensor scales, 3 products, fp32 accumulate)'}[args.precision],
         'data': 'synthetic', 'config': bench_config(args, wl, batch),
         'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps, 'api': 'MatchingCore.submit()/wait(), host buffers, 2 batches in flight',
@@ -485,9 +505,10 @@ def main():
                      'frac': attn_tflops / peaks['bf16_tflops'],
                      'traffic': traffic.get('attention_tc_self_32seq_2048', {}).get('bytes'), 'peak_source': peaks['source'] + ' bf16 burst',
                      'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops,
-                     # the kernel runs 3 tf32 MMAs per algorithmic product (fp32-grade accuracy is part of the contract);
-                     # tf32 dense rate = half the bf16 rate, so its own ceiling is bf16_peak / 6
-                     'frac_of_3xtf32_ceiling': attn_tflops / (peaks['bf16_tflops'] / 6.0) if args.precision == 'tf32x3' else None},
+                     # the kernel runs 3 MMAs per algorithmic product (fp32-grade accuracy is part of the contract): its own ceiling
+                     # is bf16_peak / 6 with tf32 operands (half rate) and bf16_peak / 3 with fp16 operands
+                     'frac_of_3x_ceiling': (attn_tflops / (peaks['bf16_tflops'] / {'tf32x3': 6.0, 'fp16x3': 3.0}[args.precision])
+                                            if args.precision != 'fp32' else None)},
         'roofline_sinkhorn': {'kernel': 'sinkhorn (%d pairs, %d iterations, one launch)' % (batch, iters), 'bound': 'hbm',
                               'achieved': sink_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                               'frac': sink_gbs / peaks['hbm_gbs'],

@@ -40,7 +40,10 @@ typedef enum og_status {
 /* arithmetic of the GEMM-shaped contractions */
 typedef enum og_precision {
   OG_PREC_FP32 = 0,             /* CUDA-core FFMA, fp32 accumulate: the exact mode                 */
-  OG_PREC_TF32X3 = 1            /* tcgen05 kind::tf32, hi/lo operand split, 3 products, fp32 accum  */
+  OG_PREC_TF32X3 = 1,           /* tcgen05 kind::tf32, hi/lo operand split, 3 products, fp32 accum  */
+  OG_PREC_FP16X3 = 2            /* tcgen05 kind::f16: fp16 hi/lo operands with power-of-two tensor scales (same 10-bit
+                                   mantissas, twice the MMA rate, half the operand bytes); GNN layers with head_dim 64,
+                                   everything else as OG_PREC_TF32X3.  Entry point: og_superglue_forward_f16          */
 } og_precision;
 
 #define OG_MAX_HIDDEN 8
@@ -120,6 +123,24 @@ int og_superglue_forward(const og_config* cfg, const float* packed_weights,
                          int64_t* matches1, float* mscores1,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* OG_PREC_FP16X3 form of the whole path: additionally takes the fp16 hi/lo split of the GNN weights and its per-tensor
+ * meta data (og_pack_f16; same element offsets as packed_weights).  packed_hi / packed_lo (tf32) are still required: the
+ * final projection and the score GEMM run the tf32 form.                                                            */
+int64_t og_f16_meta_floats(const og_config* cfg);
+int og_pack_f16(const og_config* cfg, const float* packed_weights, void* hi16, void* lo16, float* meta, void* stream);
+int og_superglue_forward_f16(const og_config* cfg, const float* packed_weights,
+                             const float* packed_hi, const float* packed_lo,
+                             const void* packed_hi16, const void* packed_lo16, const float* meta16,
+                             int batch, int n, int m,
+                             const float* kpts0, const float* kpts1,
+                             const float* side0, const float* side1,
+                             const float* desc0, const float* desc1,
+                             const float* img_wh_host,
+                             float* ctx0, float* ctx1, float* scores,
+                             int64_t* matches0, float* mscores0,
+                             int64_t* matches1, float* mscores1,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Number of kernel launches the last og_superglue_forward on this thread enqueued. */
 int og_last_forward_launches(void);
 
@@ -185,6 +206,27 @@ int og_attention_tc_fwd(const float* q, int64_t ldq, int64_t strideq,
                         const float* vthi, const float* vtlo, int64_t ldvt,
                         float* out, int64_t ldo, int64_t strideo,
                         int batch, int nq, int nk, int num_heads, int head_dim, void* stream);
+
+/* fp16 hi/lo ("3xFP16") forms of the two tensor-core operators (OG_PREC_FP16X3).  Operand scales never pass through the
+ * host: every tensor has a device scalar - its tracked max |x| (fp32 tensors) or the power-of-two scale it was written
+ * with (fp16 tensors).
+ *   og_weight_split_f16: w [rows, cols] fp32 (+ bias [rows] or NULL) -> hi16 / lo16 (fp16, same layout) and
+ *       meta[4] = {scale, max_n ||w_n||_1, max |bias|, 0}; also the way to split an activation tensor for a test.
+ *   og_amax: slot = max |x|.
+ *   og_linear_f16_fwd: args as og_linear_fwd (W, rscale, Yt ignored / must be NULL); exactly ONE output kind:
+ *       args->Y (fp32, + optional R residual, amax_out) | Yh,Yl (fp16 [rows, nout], ldy) | Yth,Ytl (fp16 [nout, rows], ldyt);
+ *       fp16 outputs are written with *scale_out (derived from a bound: a_amax * meta[1] + meta[2]).
+ *   og_attention_f16_fwd: q fp32 with its amax; khi/klo fp16 [batch*nk, ldk] with k_scale; vthi/vtlo fp16 [batch*d, ldvt]
+ *       with v_scale; head_dim 64.  swap_halves is a layout probe and must be 0.                                      */
+int og_weight_split_f16(const float* w, const float* bias, int rows, int cols, void* hi16, void* lo16, float* meta, void* stream);
+int og_amax(const float* x, int64_t n, float* slot, void* stream);
+int og_linear_f16_fwd(const og_linear_args* args, const void* Wh16, const void* Wl16, const float* w_meta, const float* a_amax,
+                      float* amax_out, float* scale_out, void* Yh, void* Yl, void* Yth, void* Ytl, int swap_halves, void* stream);
+int og_attention_f16_fwd(const float* q, int64_t ldq, int64_t strideq, const float* q_amax,
+                         const void* khi, const void* klo, int64_t ldk, const float* k_scale,
+                         const void* vthi, const void* vtlo, int64_t ldvt, const float* v_scale,
+                         float* out, int64_t ldo, int64_t strideo, float* out_amax,
+                         int batch, int nq, int nk, int num_heads, int head_dim, int swap_halves, void* stream);
 
 /* Dustbin-augmented log-domain Sinkhorn.  Replaces SuperGlue.get_matching_probs
  * (superglue.py:88-111) + log_otp_solver (optimal_transport.py:4-28).

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libopenglue_b200.so')
 
 OG_OK = 0
-OG_PREC_FP32, OG_PREC_TF32X3 = 0, 1
+OG_PREC_FP32, OG_PREC_TF32X3, OG_PREC_FP16X3 = 0, 1, 2
 OG_MAX_HIDDEN = 8
 (OG_T_KENC_W, OG_T_KENC_B, OG_T_QKV_W, OG_T_QKV_B, OG_T_FC1_W, OG_T_FC1_B, OG_T_FC2_W, OG_T_FC2_B,
  OG_T_PROJ_W, OG_T_PROJ_B, OG_T_PROJ_RMIX, OG_T_DUSTBIN) = range(12)
@@ -63,6 +63,14 @@ SYMBOLS = {
     'og_linear_tc_fwd': (_I, [C.POINTER(OgLinearArgs), _P, _P, _P, _P, _P, _P, _I, _P]),
     'og_superglue_forward': (_I, [_CFG, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    'og_superglue_forward_f16': (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float),
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    'og_f16_meta_floats': (_L, [_CFG]),
+    'og_pack_f16': (_I, [_CFG, _P, _P, _P, _P, _P]),
+    'og_weight_split_f16': (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    'og_amax': (_I, [_P, _L, _P, _P]),
+    'og_linear_f16_fwd': (_I, [C.POINTER(OgLinearArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'og_attention_f16_fwd': (_I, [_P, _L, _L, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I, _P]),
     'og_last_forward_launches': (_I, []),
     'og_set_tuning': (_I, [_I, _I]),
     'og_linear_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P]),

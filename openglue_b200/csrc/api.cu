@@ -6,6 +6,8 @@
 #include "linear_tc2.cuh"
 #include "attention_simt.cuh"
 #include "attention_tc.cuh"
+#include "linear_f16.cuh"
+#include "attention_f16.cuh"
 #include "sinkhorn.cuh"
 #include "match.cuh"
 #include "gt_matches.cuh"
@@ -74,6 +76,8 @@ struct Workspace {
   float *q, *khi, *klo, *vthi, *vtlo;     // tensor-core attention operands (OG_PREC_TF32X3)
   int64_t ldn, ldm;                       // padded row lengths of the channel-major V^T buffers
   void *sink, *match;
+  float* slots;                           // amax / scale scalars of the fp16 path (zeroed at the start of a forward pass)
+  int nslots;
   int64_t lds, sink_bytes, match_bytes, total;
 };
 
@@ -94,8 +98,10 @@ static int plan_workspace(const og_config* c, int B, int n, int m, void* base, W
   w->g = (float*)take(R * d * 4);
   w->ghi = (float*)take((int64_t)B * m * d * 4);          // tf32 split of image-1 descriptors (score GEMM B operand)
   w->glo = (float*)take((int64_t)B * m * d * 4);
-  w->ldn = align_up(n, 4); w->ldm = align_up(m, 4);
-  if (c->precision == OG_PREC_TF32X3) {
+  w->ldn = align_up(n, 8); w->ldm = align_up(m, 8);          // 16-byte rows for the fp16 form as well
+  w->nslots = 16 * c->num_layers + 16;
+  w->slots = (float*)take((int64_t)w->nslots * 4);
+  if (c->precision == OG_PREC_TF32X3 || c->precision == OG_PREC_FP16X3) {
     w->q = (float*)take(R * d * 4);
     w->khi = (float*)take(R * d * 4);
     w->klo = (float*)take(R * d * 4);
@@ -338,7 +344,8 @@ int og_criterion_fwd(const float* scores, const int64_t* gt_matches0, const int6
                           (cudaStream_t)stream);
 }
 
-int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, int B, int n, int m,
+static int forward_impl(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, const __half* W16h,
+                        const __half* W16l, const float* meta16, int B, int n, int m,
                          const float* kpts0,
                          const float* kpts1, const float* side0, const float* side1, const float* desc0,
                          const float* desc1, const float* img_wh, float* ctx0, float* ctx1, float* scores,
@@ -349,13 +356,18 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi
   OG_CHECK_ARG(Wp && kpts0 && kpts1 && desc0 && desc1 && img_wh && scores && workspace, "forward: null pointer");
   OG_CHECK_ARG(cfg->side_info_size == 0 || (side0 && side1), "forward: side info missing");
   OG_CHECK_ARG(B > 0 && n > 0 && m > 0, "forward: batch, n, m must be positive");
-  OG_CHECK_ARG(cfg->precision == OG_PREC_FP32 || (Whi && Wlo), "forward: OG_PREC_TF32X3 needs packed_hi / packed_lo");
-  const bool tcp = (cfg->precision == OG_PREC_TF32X3) && cfg->descriptor_dim >= 32;   // K >= 32 for the tcgen05 tiles
+  OG_CHECK_ARG(cfg->precision == OG_PREC_FP32 || (Whi && Wlo), "forward: the tensor-core modes need packed_hi / packed_lo");
+  OG_CHECK_ARG(cfg->precision != OG_PREC_FP16X3 || (W16h && W16l && meta16), "forward: OG_PREC_FP16X3 needs the fp16 weight split (og_pack_f16)");
+  const bool tcp = (cfg->precision != OG_PREC_FP32) && cfg->descriptor_dim >= 32;   // K >= 32 for the tcgen05 tiles
+  // fp16 hi/lo form of the GNN (projections, attention, message MLP): head_dim 64, d a multiple of 64; everything else
+  // (Dh = 32, the final projection, the score GEMM) runs the tf32 hi/lo form - same accuracy class
+  const bool f16p = tcp && cfg->precision == OG_PREC_FP16X3 && cfg->descriptor_dim % 64 == 0 &&
+                    cfg->descriptor_dim / cfg->num_heads == 64;
   auto WH = [&](int64_t off) { return tcp ? Whi + off : nullptr; };
   auto WL = [&](int64_t off) { return tcp ? Wlo + off : nullptr; };
   OG_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream_;
-  const int prec = cfg->precision;
+  const int prec = cfg->precision == OG_PREC_FP16X3 ? OG_PREC_TF32X3 : cfg->precision;     // what the non-f16 launches run as
   const Layout L = make_layout(cfg);
   Workspace w;
   rc = plan_workspace(cfg, B, n, m, workspace, &w);
@@ -452,7 +464,109 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi
     return attention_tc_launch(a, w.khi + (int64_t)krow0 * d, w.klo + (int64_t)krow0 * d, d, w.vthi + voff, w.vtlo + voff,
                                ldv, dh, st);
   };
+  // ---- fp16 hi/lo form of the GNN (OG_PREC_FP16X3; csrc/linear_f16.cuh, csrc/attention_f16.cuh) ----
+  // Every activation tensor has a device slot with its tracked amax (fp32 tensors) or the scale it was written with (fp16
+  // K / V^T); a consumer derives its operand scale from the producers' slots, so no scale ever passes through the host.
+  int nslot = 0;
+  auto new_slot = [&]() -> float* { return w.slots + (nslot < w.nslots - 1 ? nslot++ : w.nslots - 1); };
+  float *sx0 = nullptr, *sx1 = nullptr;                      // amax slots of the current x0 / x1
+  __half* kh16 = reinterpret_cast<__half*>(w.khi); __half* kl16 = reinterpret_cast<__half*>(w.klo);
+  __half* vth16 = reinterpret_cast<__half*>(w.vthi); __half* vtl16 = reinterpret_cast<__half*>(w.vtlo);
+  if (f16p) {
+    OG_CUDA(cudaMemsetAsync(w.slots, 0, (size_t)w.nslots * 4, st));
+    sx0 = sx1 = new_slot();
+    const int64_t nx = (int64_t)R * d;
+    amax_kernel<<<(unsigned)std::min<int64_t>((nx + 2047) / 2048, 1184), 256, 0, st>>>(w.x, nx, sx0);
+    OG_LAUNCH_CHECK("amax_kernel");
+    launch_counter()++;
+  }
+  auto M16 = [&](int l, int t) { return meta16 + ((int64_t)l * 5 + t) * 4; };
+  auto gemm16 = [&](const float* A, int64_t lda, int k1, const float* A2, int64_t lda2, int k2, int64_t woff, const float* bias,
+                    int rows, int nout, const float* am0, const float* am1, const float* am2, const float* meta) {
+    F16LinearArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = A; g.lda = lda; g.k1 = k1; g.A2 = A2; g.lda2 = lda2; g.k2 = k2; g.bias = bias; g.rows = rows; g.nout = nout; g.batch = 1;
+    g.alpha = 1.f; g.amax_in[0] = am0; g.amax_in[1] = am1; g.amax_in[2] = am2; g.w_meta = meta;
+    (void)woff;
+    return g;
+  };
+  auto run16 = [&](const F16LinearArgs& g, int64_t woff) -> int {
+    const int K = g.k1 + g.k2;
+    if (!linear_f16_eligible(g, W16h + woff, W16l + woff, K)) return fail(OG_EUNSUPPORTED, "forward: a layer is not tileable by the fp16 GEMM");
+    return linear_f16_launch(g, W16h + woff, W16l + woff, K, g.nout, st);
+  };
+  struct SeqSlots { float *q, *k, *v, *o; };
+  auto project_f16 = [&](int l, int qrow0, int nq_rows, int srow0, int ns, int sbatch, float* aq0, float* aq1, float* as0, float* as1,
+                         SeqSlots& ss) -> int {
+    int r;
+    ss.q = new_slot(); ss.k = new_slot(); ss.v = new_slot(); ss.o = new_slot();
+    F16LinearArgs gq = gemm16(w.x + (int64_t)qrow0 * d, d, d, nullptr, 0, 0, L.qkv_w[l], Wp + L.qkv_b[l], nq_rows, d, aq0, aq1, nullptr, M16(l, 0));
+    gq.Y = w.q + (int64_t)qrow0 * d; gq.ldy = d; gq.amax_out = ss.q;
+    if ((r = run16(gq, L.qkv_w[l])) != OG_OK) return r;
+    F16LinearArgs gk = gemm16(w.x + (int64_t)srow0 * d, d, d, nullptr, 0, 0, 0, Wp + L.qkv_b[l] + d, sbatch * ns, d, as0, as1, nullptr, M16(l, 1));
+    gk.Yh = kh16 + (int64_t)srow0 * d; gk.Yl = kl16 + (int64_t)srow0 * d; gk.ldy = d; gk.scale_out = ss.k;
+    if ((r = run16(gk, L.qkv_w[l] + (int64_t)d * d)) != OG_OK) return r;
+    const int64_t ldv = (srow0 == 0) ? w.ldn : w.ldm;
+    const int64_t voff = (srow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
+    F16LinearArgs gv = gemm16(w.x + (int64_t)srow0 * d, d, d, nullptr, 0, 0, 0, Wp + L.qkv_b[l] + 2 * d, ns, d, as0, as1, nullptr, M16(l, 2));
+    gv.batch = sbatch; gv.strideA = (int64_t)ns * d; gv.Yth = vth16 + voff; gv.Ytl = vtl16 + voff; gv.ldyt = ldv; gv.strideYt = (int64_t)d * ldv;
+    gv.scale_out = ss.v;
+    return run16(gv, L.qkv_w[l] + 2 * (int64_t)d * d);
+  };
+  auto attend_f16 = [&](int qrow0, int nq, int krow0, int nk, int batch, const SeqSlots& ss) -> int {
+    const int64_t ldv = (krow0 == 0) ? w.ldn : w.ldm;
+    const int64_t voff = (krow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
+    TcAttnArgs a{w.q + (int64_t)qrow0 * d, d, (int64_t)nq * d, w.o + (int64_t)qrow0 * d, d, (int64_t)nq * d,
+                 batch, nq, nk, H, d, (float)pow((double)dh, -0.5)};
+    F16AttnScales sc{ss.q, ss.k, ss.v, ss.o, 0};
+    return attention_f16_launch(a, sc, kh16 + (int64_t)krow0 * d, kl16 + (int64_t)krow0 * d, d, vth16 + voff, vtl16 + voff, ldv, dh, st);
+  };
+  auto mlp_f16 = [&](int l, int row0, int rows, float* ax0, float* ax1, float* ao, float** sx_new) -> int {
+    float* sh = new_slot();
+    float* sn = new_slot();
+    float* xr = w.x + (int64_t)row0 * d;
+    F16LinearArgs g1 = gemm16(xr, d, d, w.o + (int64_t)row0 * d, d, d, 0, Wp + L.fc1_b[l], rows, 2 * d, ax0, ax1, ao, M16(l, 3));
+    g1.relu = 1; g1.Y = w.hid + (int64_t)row0 * 2 * d; g1.ldy = 2 * d; g1.amax_out = sh;
+    int r = run16(g1, L.fc1_w[l]);
+    if (r != OG_OK) return r;
+    F16LinearArgs g2 = gemm16(w.hid + (int64_t)row0 * 2 * d, 2 * d, 2 * d, nullptr, 0, 0, 0, Wp + L.fc2_b[l], rows, d, sh, nullptr, nullptr, M16(l, 4));
+    g2.R = xr; g2.ldr = d; g2.Y = xr; g2.ldy = d; g2.amax_out = sn;
+    *sx_new = sn;
+    return run16(g2, L.fc2_w[l]);
+  };
   for (int l = 0; l < cfg->num_layers; ++l) {
+    if (f16p) {
+      SeqSlots ss;
+      float* sn = nullptr;
+      if (l % 2 == 0) {                                    // self
+        if (n == m) {
+          if ((rc = project_f16(l, 0, R, 0, n, 2 * B, sx0, sx1, sx0, sx1, ss)) != OG_OK) return rc;
+          if ((rc = attend_f16(0, n, 0, n, 2 * B, ss)) != OG_OK) return rc;
+          if ((rc = mlp_f16(l, 0, R, sx0, sx1, ss.o, &sn)) != OG_OK) return rc;
+          sx0 = sx1 = sn;
+        } else {
+          SeqSlots s1;
+          if ((rc = project_f16(l, 0, R0, 0, n, B, sx0, nullptr, sx0, nullptr, ss)) != OG_OK) return rc;
+          if ((rc = attend_f16(0, n, 0, n, B, ss)) != OG_OK) return rc;
+          if ((rc = project_f16(l, R0, R1, R0, m, B, sx1, nullptr, sx1, nullptr, s1)) != OG_OK) return rc;
+          if ((rc = attend_f16(R0, m, R0, m, B, s1)) != OG_OK) return rc;
+          float *sa = nullptr, *sb = nullptr;
+          if ((rc = mlp_f16(l, 0, R0, sx0, nullptr, ss.o, &sa)) != OG_OK) return rc;
+          if ((rc = mlp_f16(l, R0, R1, sx1, nullptr, s1.o, &sb)) != OG_OK) return rc;
+          sx0 = sa; sx1 = sb;
+        }
+      } else {                                             // cross: SEQUENTIAL (attention_gnn.py:74-77)
+        if ((rc = project_f16(l, 0, R0, R0, m, B, sx0, nullptr, sx1, nullptr, ss)) != OG_OK) return rc;
+        if ((rc = attend_f16(0, n, R0, m, B, ss)) != OG_OK) return rc;
+        if ((rc = mlp_f16(l, 0, R0, sx0, nullptr, ss.o, &sn)) != OG_OK) return rc;
+        sx0 = sn;
+        if ((rc = project_f16(l, R0, R1, 0, n, B, sx1, nullptr, sx0, nullptr, ss)) != OG_OK) return rc;     // k, v of the UPDATED image 0
+        if ((rc = attend_f16(R0, m, 0, n, B, ss)) != OG_OK) return rc;
+        if ((rc = mlp_f16(l, R0, R1, sx1, nullptr, ss.o, &sn)) != OG_OK) return rc;
+        sx1 = sn;
+      }
+      continue;
+    }
     if (tca_ok) {
       if (l % 2 == 0) {                                    // self
         if (n == m) {
@@ -527,6 +641,111 @@ int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi
     if (rc != OG_OK) return rc;
   }
   return OG_OK;
+}
+
+int og_superglue_forward(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, int B, int n, int m,
+                         const float* kpts0, const float* kpts1, const float* side0, const float* side1, const float* desc0,
+                         const float* desc1, const float* img_wh, float* ctx0, float* ctx1, float* scores,
+                         int64_t* matches0, float* mscores0, int64_t* matches1, float* mscores1, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  if (cfg && cfg->precision == OG_PREC_FP16X3) return fail(OG_EINVAL, "forward: OG_PREC_FP16X3 takes og_superglue_forward_f16");
+  return forward_impl(cfg, Wp, Whi, Wlo, nullptr, nullptr, nullptr, B, n, m, kpts0, kpts1, side0, side1, desc0, desc1, img_wh, ctx0, ctx1,
+                      scores, matches0, mscores0, matches1, mscores1, workspace, workspace_bytes, stream);
+}
+
+int og_superglue_forward_f16(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, const void* W16h,
+                             const void* W16l, const float* meta16, int B, int n, int m,
+                             const float* kpts0, const float* kpts1, const float* side0, const float* side1, const float* desc0,
+                             const float* desc1, const float* img_wh, float* ctx0, float* ctx1, float* scores,
+                             int64_t* matches0, float* mscores0, int64_t* matches1, float* mscores1, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  return forward_impl(cfg, Wp, Whi, Wlo, static_cast<const __half*>(W16h), static_cast<const __half*>(W16l), meta16, B, n, m, kpts0, kpts1,
+                      side0, side1, desc0, desc1, img_wh, ctx0, ctx1, scores, matches0, mscores0, matches1, mscores1, workspace,
+                      workspace_bytes, stream);
+}
+
+int64_t og_f16_meta_floats(const og_config* cfg) {
+  if (check_config(cfg) != OG_OK) return -1;
+  return (int64_t)cfg->num_layers * 5 * 4;
+}
+
+int og_weight_split_f16(const float* w, const float* bias, int rows, int cols, void* hi16, void* lo16, float* meta, void* stream) {
+  OG_CHECK_ARG(w && hi16 && lo16 && meta && rows > 0 && cols > 0, "weight_split_f16: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  OG_CUDA(cudaMemsetAsync(meta, 0, 4 * sizeof(float), st));
+  weight_meta_kernel<<<cdiv(rows, 8), 256, 0, st>>>(w, bias, rows, cols, meta);
+  OG_LAUNCH_CHECK("weight_meta_kernel");
+  const int64_t nel = (int64_t)rows * cols;
+  split_f16_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(w, static_cast<__half*>(hi16), static_cast<__half*>(lo16), nel, meta);
+  OG_LAUNCH_CHECK("split_f16_kernel");
+  finish_meta_kernel<<<1, 1, 0, st>>>(meta);
+  OG_LAUNCH_CHECK("finish_meta_kernel");
+  return OG_OK;
+}
+
+int og_pack_f16(const og_config* cfg, const float* Wp, void* hi16, void* lo16, float* meta, void* stream) {
+  int rc = check_config(cfg);
+  if (rc != OG_OK) return rc;
+  OG_CHECK_ARG(Wp && hi16 && lo16 && meta, "pack_f16: null pointer");
+  const Layout L = make_layout(cfg);
+  const int64_t d = cfg->descriptor_dim;
+  __half* h = static_cast<__half*>(hi16); __half* lo = static_cast<__half*>(lo16);
+  for (int l = 0; l < cfg->num_layers; ++l) {
+    struct T { int64_t woff, boff; int rows, cols; } ts[5] = {
+      {L.qkv_w[l], L.qkv_b[l], (int)d, (int)d}, {L.qkv_w[l] + d * d, L.qkv_b[l] + d, (int)d, (int)d},
+      {L.qkv_w[l] + 2 * d * d, L.qkv_b[l] + 2 * d, (int)d, (int)d},
+      {L.fc1_w[l], L.fc1_b[l], (int)(2 * d), (int)(2 * d)}, {L.fc2_w[l], L.fc2_b[l], (int)d, (int)(2 * d)}};
+    for (int t = 0; t < 5; ++t)
+      if ((rc = og_weight_split_f16(Wp + ts[t].woff, Wp + ts[t].boff, ts[t].rows, ts[t].cols, h + ts[t].woff, lo + ts[t].woff,
+                                    meta + ((int64_t)l * 5 + t) * 4, stream)) != OG_OK) return rc;
+  }
+  return OG_OK;
+}
+
+int og_amax(const float* x, int64_t n, float* slot, void* stream) {
+  OG_CHECK_ARG(x && slot && n > 0, "amax: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  OG_CUDA(cudaMemsetAsync(slot, 0, sizeof(float), st));
+  amax_kernel<<<(unsigned)std::min<int64_t>((n + 2047) / 2048, 1184), 256, 0, st>>>(x, n, slot);
+  OG_LAUNCH_CHECK("amax_kernel");
+  return OG_OK;
+}
+
+int og_linear_f16_fwd(const og_linear_args* a, const void* Wh16, const void* Wl16, const float* w_meta, const float* a_amax,
+                      float* amax_out, float* scale_out, void* Yh, void* Yl, void* Yth, void* Ytl, int swap_halves, void* stream) {
+  OG_CHECK_ARG(a && a->A && Wh16 && Wl16 && w_meta && a_amax, "linear_f16: null pointer");
+  OG_CHECK_ARG(a->rows > 0 && a->nout > 0 && a->batch > 0 && a->k1 > 0 && a->k2 >= 0, "linear_f16: bad sizes");
+  OG_CHECK_ARG(!a->rscale && !a->Yt, "linear_f16: rscale / fp32 transposed outputs are not part of the fp16 form");
+  F16LinearArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = a->A; g.lda = a->lda; g.strideA = a->strideA; g.A2 = a->A2; g.lda2 = a->lda2; g.strideA2 = a->strideA2; g.k1 = a->k1; g.k2 = a->k2;
+  if (a->strideW && a->strideW % a->ldw != 0) return fail(OG_EUNSUPPORTED, "linear_f16: strideW must be a multiple of ldw");
+  g.b_rows_per_batch = a->strideW ? (int)(a->strideW / a->ldw) : 0;
+  g.bias = a->bias; g.rows = a->rows; g.nout = a->nout; g.batch = a->batch; g.alpha = a->alpha; g.relu = a->relu;
+  g.R = a->R; g.ldr = a->ldr; g.strideR = a->strideR;
+  g.Y = a->Y; g.ldy = a->ldy; g.strideY = a->strideY;
+  g.Yh = static_cast<__half*>(Yh); g.Yl = static_cast<__half*>(Yl);
+  g.Yth = static_cast<__half*>(Yth); g.Ytl = static_cast<__half*>(Ytl); g.ldyt = a->ldyt; g.strideYt = a->strideYt;
+  g.amax_in[0] = a_amax; g.w_meta = w_meta; g.amax_out = amax_out; g.scale_out = scale_out; g.swap_halves = swap_halves;
+  const __half* bh = static_cast<const __half*>(Wh16); const __half* bl = static_cast<const __half*>(Wl16);
+  if (!linear_f16_eligible(g, bh, bl, a->ldw))
+    return fail(OG_EUNSUPPORTED, "linear_f16: needs K >= 64, 16-byte aligned rows, exactly one output kind (Y | Yh,Yl | Yth,Ytl)");
+  const int64_t brows = a->strideW ? (int64_t)g.b_rows_per_batch * a->batch : a->nout;
+  return linear_f16_launch(g, bh, bl, a->ldw, brows, (cudaStream_t)stream);
+}
+
+int og_attention_f16_fwd(const float* q, int64_t ldq, int64_t strideq, const float* q_amax, const void* khi, const void* klo,
+                         int64_t ldk, const float* k_scale, const void* vthi, const void* vtlo, int64_t ldvt, const float* v_scale,
+                         float* out, int64_t ldo, int64_t strideo, float* out_amax, int batch, int nq, int nk, int num_heads,
+                         int head_dim, int swap_halves, void* stream) {
+  OG_CHECK_ARG(q && q_amax && khi && klo && k_scale && vthi && vtlo && v_scale && out, "attention_f16: null pointer");
+  OG_CHECK_ARG(batch > 0 && nq > 0 && nk > 0 && num_heads > 0, "attention_f16: bad sizes");
+  if (!attention_f16_eligible(head_dim, ldq, ldk, ldvt, ldo))
+    return fail(OG_EUNSUPPORTED, "attention_f16: head_dim 64 and 16-byte aligned rows required");
+  TcAttnArgs a{q, ldq, strideq, out, ldo, strideo, batch, nq, nk, num_heads, num_heads * head_dim, (float)pow((double)head_dim, -0.5)};
+  F16AttnScales sc{q_amax, k_scale, v_scale, out_amax, swap_halves};
+  return attention_f16_launch(a, sc, static_cast<const __half*>(khi), static_cast<const __half*>(klo), ldk,
+                              static_cast<const __half*>(vthi), static_cast<const __half*>(vtlo), ldvt, head_dim, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -3,8 +3,10 @@
 // Descriptor bit layouts follow the PTX ISA (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace og {
 #ifdef OG_TRACE
@@ -272,6 +274,56 @@ __device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t&
 #endif
 }
 
+// ----------------------------------------------------------------------------- fp16 hi/lo operands ("3xFP16", kind::f16)
+// fp16 has tf32's 10 explicit mantissa bits at twice the MMA rate and half the operand bytes; what it lacks is range
+// (2^-14 normal .. 65504).  Every operand tensor therefore carries a power-of-two scale that puts a bound on max|x| into
+// [2^14, 2^15): hi = fp16(x s), lo = fp16(x s - hi).  |lo| <= 2^-11 |hi| stays a normal half for |x s| >= 2^-3 and is
+// otherwise resolved to the subnormal spacing 2^-24, so the pair represents x s to max(2^-22 |x s|, 2^-25): 40 bits below the bound.
+// Products of halves are exact in fp32; the scales are undone exactly in the epilogue (powers of two).
+
+// Instruction descriptor, kind::f16 with fp16 operands, fp32 accumulate, A and B K-major (a_format = b_format = 0: F16).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem, packed halves: 32-bit column c = K elements 2c (low half), 2c+1] . B[smem desc]; K = 16 per instruction
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+// power-of-two scale for a tensor whose magnitudes are bounded by `bound` (>= 0): bound * scale in [2^14, 2^15)
+__host__ __device__ __forceinline__ float f16_scale_for(float bound) {
+#ifdef __CUDA_ARCH__
+  uint32_t e = (__float_as_uint(bound) >> 23) & 0xffu;
+#else
+  uint32_t bits; memcpy(&bits, &bound, 4); uint32_t e = (bits >> 23) & 0xffu;
+#endif
+  e = e < 87u ? 87u : (e > 187u ? 187u : e);                 // |bound| outside 2^-40 .. 2^60: clamp (all-zero tensors, garbage)
+  const uint32_t sb = (268u - e) << 23;                        // 2^(14 - (e - 127))
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(sb);
+#else
+  float r; memcpy(&r, &sb, 4); return r;
+#endif
+}
+// two already-scaled values -> packed hi halves and packed lo halves (element 0 in the low 16 bits)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// non-negative float max through its bit pattern (amax tracking; the slot is zeroed at the start of a forward pass)
+__device__ __forceinline__ void atomic_amax(float* slot, float v) { atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v)); }
+
 // ----------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -317,6 +369,38 @@ inline int make_tmap_3d(CUtensorMap* map, const float* base, uint64_t batch, uin
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OG_ECUDA, "cuTensorMapEncodeTiled (3d) failed (%d)", (int)r);
+  return OG_OK;
+}
+
+// fp16 row-major tensor [rows, cols] with row stride ld (ELEMENTS); box = 64 halves (128 bytes) x box_rows, 128B swizzle.
+inline int make_tmap_2d_f16(CUtensorMap* map, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(OG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OG_ECUDA, "cuTensorMapEncodeTiled (f16) failed (%d): rows=%llu cols=%llu ld=%llu", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return OG_OK;
+}
+// 3-D fp16 tensor [batch, rows, cols]; box = 64 cols x box_rows x 1 (TMA stores that clip at the batch boundary)
+inline int make_tmap_3d_f16(CUtensorMap* map, const __half* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint64_t bstride, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return fail(OG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (batch <= 1 || bstride == 0) { batch = 1; bstride = rows * ld; }
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * sizeof(__half), bstride * sizeof(__half)};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OG_ECUDA, "cuTensorMapEncodeTiled (f16, 3d) failed (%d)", (int)r);
   return OG_OK;
 }
 

@@ -55,7 +55,8 @@ class SuperGlue(nn.Module):
     """B200-native matching core behind the reference's module API.
 
     Extra (optional) config keys, ignored by the reference: ``precision`` ('tf32x3' (default): tcgen05 tensor
-    cores with error-compensated tf32, | 'fp32': CUDA-core FFMA everywhere),
+    cores with error-compensated tf32 | 'fp16x3': the same three-product scheme on fp16 hi/lo operands with
+    power-of-two tensor scales, twice the MMA rate | 'fp32': CUDA-core FFMA everywhere),
     ``match_threshold`` (used by :class:`MatchingCore`).
     """
 
@@ -86,6 +87,7 @@ class SuperGlue(nn.Module):
         self._packed_key = None
         self._packed_hi: Optional[torch.Tensor] = None
         self._packed_lo: Optional[torch.Tensor] = None
+        self._packed_h16 = self._packed_l16 = self._meta16 = None
         self._workspace: Optional[torch.Tensor] = None
         self._ogcfg: Optional[_cabi.OgConfig] = None
         self.last_launches = 0
@@ -96,7 +98,8 @@ class SuperGlue(nn.Module):
 
     # ------------------------------------------------------------------ weights
     def _precision(self) -> int:
-        return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3}[self.config.get('precision', 'tf32x3')]
+        return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3,
+                'fp16x3': _cabi.OG_PREC_FP16X3}[self.config.get('precision', 'tf32x3')]
 
     def og_config(self) -> _cabi.OgConfig:
         return _cabi.make_config(self.config, self.config.get('match_threshold', 0.2), self._precision())
@@ -146,14 +149,24 @@ class SuperGlue(nn.Module):
             self._ogcfg = self.og_config()
             self._packed = pack_weights(self.state_dict(), self.config, self._ogcfg).to(device)
             self._packed_hi = self._packed_lo = None
+            self._packed_h16 = self._packed_l16 = self._meta16 = None
             self._bump_alloc()
-            if self._precision() == _cabi.OG_PREC_TF32X3:      # operand split for the tcgen05 kernels
+            if self._precision() != _cabi.OG_PREC_FP32:        # operand split for the tcgen05 kernels
                 self._packed_hi, self._packed_lo = torch.empty_like(self._packed), torch.empty_like(self._packed)
                 with torch.cuda.device(device):
                     _cabi.check(_cabi.lib().og_split_tf32(
                         C.c_void_p(self._packed.data_ptr()), C.c_void_p(self._packed_hi.data_ptr()),
                         C.c_void_p(self._packed_lo.data_ptr()), self._packed.numel(),
                         C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), 'og_split_tf32')
+            if self._precision() == _cabi.OG_PREC_FP16X3:      # fp16 hi/lo split of the GNN weights + per-tensor scales / norms
+                lib = _cabi.lib()
+                self._packed_h16 = torch.zeros(self._packed.numel(), dtype=torch.float16, device=device)
+                self._packed_l16 = torch.zeros_like(self._packed_h16)
+                self._meta16 = torch.zeros(max(int(lib.og_f16_meta_floats(self._ogcfg)), 4), dtype=torch.float32, device=device)
+                with torch.cuda.device(device):
+                    _cabi.check(lib.og_pack_f16(self._ogcfg, C.c_void_p(self._packed.data_ptr()), C.c_void_p(self._packed_h16.data_ptr()),
+                                                C.c_void_p(self._packed_l16.data_ptr()), C.c_void_p(self._meta16.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(device).cuda_stream)), 'og_pack_f16')
             self._packed_key = key
         return self._packed
 
@@ -228,10 +241,13 @@ class SuperGlue(nn.Module):
                 out.update(matches0=m0, matching_scores0=ms0, matches1=m1, matching_scores1=ms1)
             wh = (C.c_float * 4)(w0, h0, w1, h1)
             ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-            rc = lib.og_superglue_forward(cfg, ptr(packed), ptr(self._packed_hi), ptr(self._packed_lo), B, n, m, ptr(k0), ptr(k1), ptr(s0), ptr(s1), ptr(d0),
-                                          ptr(d1), wh, ptr(ctx0), ptr(ctx1), ptr(scores), ptr(m0), ptr(ms0),
-                                          ptr(m1), ptr(ms1), ptr(self._workspace), ws_bytes,
-                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            tail = (B, n, m, ptr(k0), ptr(k1), ptr(s0), ptr(s1), ptr(d0), ptr(d1), wh, ptr(ctx0), ptr(ctx1), ptr(scores), ptr(m0), ptr(ms0),
+                    ptr(m1), ptr(ms1), ptr(self._workspace), ws_bytes, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if cfg.precision == _cabi.OG_PREC_FP16X3:
+                rc = lib.og_superglue_forward_f16(cfg, ptr(packed), ptr(self._packed_hi), ptr(self._packed_lo), ptr(self._packed_h16),
+                                                  ptr(self._packed_l16), ptr(self._meta16), *tail)
+            else:
+                rc = lib.og_superglue_forward(cfg, ptr(packed), ptr(self._packed_hi), ptr(self._packed_lo), *tail)
             _cabi.check(rc, 'og_superglue_forward')
             self.last_launches = lib.og_last_forward_launches()
         return out

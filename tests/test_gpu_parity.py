@@ -115,7 +115,7 @@ def test_forward_matches_reference_c1(golden, name):
 
 
 # --------------------------------------------------------------------------- the configs the numbers are quoted on
-@pytest.mark.parametrize('precision,pair', [('tf32x3', 1), ('tf32x3', 0), ('fp32', 1)])
+@pytest.mark.parametrize('precision,pair', [('fp16x3', 1), ('fp16x3', 0), ('tf32x3', 1), ('tf32x3', 0), ('fp32', 1)])
 @pytest.mark.parametrize('name', GOLDEN_BIG)
 def test_forward_matches_reference_big(golden, name, precision, pair):
     """BASELINE.json configs[1] (C2), [2] (C3, headline: the 16 pairs bench.py times on rank 0) and [4] (C5, 18 stages,
@@ -173,8 +173,10 @@ def test_forward_matches_reference_big(golden, name, precision, pair):
     (2, 256, 1100, dict(descriptor_dim=64, num_stages=1, num_iters=15, reg=0.5, use_offset=True,
                         residual=False), 'flat'),                                     # V=16 path, reg != 1
     (1, 4096, 1024, dict(descriptor_dim=128, num_stages=1, num_iters=50, side_info_size=6), 'planted'),   # configs[4] shape
+    (2, 330, 197, dict(descriptor_dim=256, num_stages=2, num_iters=30), 'planted'),    # head_dim 64 (the fp16x3 GNN path), ragged n != m
+    (1, 200, 200, dict(descriptor_dim=256, num_stages=3, num_iters=20, use_offset=True), 'flat'),        # head_dim 64, n == m (joint self layers)
 ])
-@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'fp16x3'])
 def test_forward_matches_oracle(batch, n, m, kw, family, precision):
     cfg = default_config(**kw)
     sd = synthetic_state_dict(cfg, seed=3)
