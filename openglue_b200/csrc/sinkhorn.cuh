@@ -12,8 +12,9 @@
 // column contribution, and the augmented (n+1) x (m+1) matrix is never materialised: the
 // dustbin row and column are the constant dustbin score and are generated in registers.
 //
-// Decomposition: pair b is cut into SP strips of whole rows, one CTA per strip, one warp per
-// row (float4 per lane, V float4s per lane => m <= 128 V).  Column sums are reduced
+// Decomposition: pair b is cut into SP strips of whole rows, one CTA per strip; a row is shared by W warps
+// (a warp owns 128 V consecutive columns: V float4s per lane => m <= 128 V W <= 8192; the warps of a row
+// combine their (max, sum) through shared memory and one named barrier per row).  Column sums are reduced
 // warp -> CTA (shared memory) -> grid (per-strip partials in global memory, double buffered),
 // with one grid-wide barrier per iteration; every CTA of a pair then rebuilds v redundantly
 // in a fixed order (deterministic, no atomics on data).
@@ -57,7 +58,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 }
 
 // --- shared-memory row ring fed by bulk async copies (TMA 1-D): decouples HBM latency from the math ---
-constexpr int SINK_SLOTS = 2;             // rows in flight per warp (plus the one being processed in registers)
 
 __device__ __forceinline__ uint32_t sink_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void sink_mbar_init(uint64_t* bar) {
@@ -76,18 +76,26 @@ __device__ __forceinline__ void sink_mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-template <int V>
-__global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a) {
+// V: float4s per lane of a warp's column segment (C = 128 V columns);  W: warps that share one row (a row group covers
+// W C columns; the warps exchange (max, sum) of their segments through shared memory and one named barrier per row);
+// SLOTS: ring depth per warp.  Configurations with V <= 8 need <= 128 registers and <= 106 KB of shared memory: two CTAs
+// per SM, so one CTA streams while the other sits in its per-iteration reduction / barrier phase.
+template <int V, int W, int SLOTS>
+__global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_kernel(SinkArgs a) {
   extern __shared__ __align__(128) float og_sink_smem[];
-  constexpr int SLOT = 128 * V;                        // floats per ring slot (one padded row)
-  constexpr int VD = 128 * V;                          // v_s[VD] = v of the dustbin column
-  float* v_s = og_sink_smem;                           // [128 V + 4]  v_j for j < m, -inf for m <= j < 128 V (masks the padding
-                                                       //              columns in the sweep without per-element selects), v_dustbin
-  float* red = og_sink_smem + VD + 4;                  // [SINK_WARPS][mpad]
-  float* ring = red + SINK_WARPS * a.mpad;             // [SINK_WARPS][SINK_SLOTS][SLOT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SINK_WARPS * SINK_SLOTS * SLOT);   // [SINK_WARPS][SINK_SLOTS]
+  constexpr int C = 128 * V;                           // columns of one warp's segment = floats per ring slot
+  constexpr int MC = W * C;                            // columns a row group covers (m <= MC)
+  constexpr int G = SINK_WARPS / W;                    // row groups = rows in progress per CTA
+  float* v_s = og_sink_smem;                           // [MC + 4]  v_j for j < m, -inf for m <= j < MC (masks the padding
+                                                       //           columns in the sweep without per-element selects), v_s[MC] = v_dustbin
+  float* red = og_sink_smem + MC + 4;                  // [G][mpad]
+  float* ring = red + G * a.mpad;                      // [SINK_WARPS][SLOTS][C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + SINK_WARPS * SLOTS * C);   // [SINK_WARPS][SLOTS]
+  float2* xr = reinterpret_cast<float2*>(bars + SINK_WARPS * SLOTS);             // [2][G][W] (max, sum) of a segment
   const int b = blockIdx.x / a.SP, strip = blockIdx.x % a.SP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp / W, sub = warp % W;
+  const int c0 = sub * C;                              // first column of this warp's segment
   const int n = a.n, m = a.m;
   const int r0 = strip * a.rows_per_strip;
   const int r1 = min(r0 + a.rows_per_strip, n + 1);
@@ -96,63 +104,72 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
   const bool unit_reg = (a.reg == 1.0f);
   const float dz = unit_reg ? __ldg(a.dustbin) : __fdiv_rn(__ldg(a.dustbin), a.reg);   // Z = M / reg
   const float a_reg = expf(a.norm), a_last = expf(a.log_a_last);
-  const uint32_t row_bytes = (uint32_t)(((m + 3) / 4) * 16);      // <= 4 * lds: stays inside the padded row
-  float* my_ring = ring + warp * SINK_SLOTS * SLOT;
-  uint64_t* my_bars = bars + warp * SINK_SLOTS;
+  const int seg_cols = min(m, c0 + C) - c0;            // <= 0: this warp's segment lies beyond the last column
+  const bool has_seg = seg_cols > 0;
+  const uint32_t seg_bytes = has_seg ? (uint32_t)(((seg_cols + 3) / 4) * 16) : 0u;     // <= 4 * (lds - c0): inside the padded row
+  float* my_ring = ring + warp * SLOTS * C;
+  uint64_t* my_bars = bars + warp * SLOTS;
 
   if (lane == 0) {
-    for (int sl = 0; sl < SINK_SLOTS; ++sl) sink_mbar_init(&my_bars[sl]);
+    for (int sl = 0; sl < SLOTS; ++sl) sink_mbar_init(&my_bars[sl]);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int j = tid; j < VD; j += blockDim.x) v_s[j] = (j < m) ? 0.f : -CUDART_INF_F;
-  if (tid == 0) v_s[VD] = 0.f;
+  for (int j = tid; j < MC; j += blockDim.x) v_s[j] = (j < m) ? 0.f : -CUDART_INF_F;
+  if (tid == 0) v_s[MC] = 0.f;
   __syncthreads();
 
   uint32_t issued = 0, consumed = 0;                   // per-warp ring counters (real rows only)
-  auto prefetch_first = [&]() {                        // first SINK_SLOTS rows of this warp's strip share
-    if (lane == 0) {
-      for (int sl = 0; sl < SINK_SLOTS; ++sl) {
-        const int row = r0 + warp + sl * SINK_WARPS;
-        if (row < r1_real) { sink_row_copy(my_ring + (issued % SINK_SLOTS) * SLOT, Sb + (int64_t)row * a.lds, row_bytes, &my_bars[issued % SINK_SLOTS]); }
-        if (row < r1_real) ++issued;
+  auto prefetch_first = [&]() {                        // first SLOTS rows of this warp's group
+    if (lane == 0 && has_seg) {
+      for (int sl = 0; sl < SLOTS; ++sl) {
+        const int row = r0 + grp + sl * G;
+        if (row < r1_real) {
+          sink_row_copy(my_ring + (issued % SLOTS) * C, Sb + (int64_t)row * a.lds + c0, seg_bytes, &my_bars[issued % SLOTS]);
+          ++issued;
+        }
       }
     }
   };
-  // fetch row `row` of this warp into registers; refill the slot with the row SINK_SLOTS ahead
+  // fetch this warp's segment of row `row` into registers; refill the slot with the row SLOTS ahead
   auto take_row = [&](int row, float4 (&z)[V]) {
     if (row < n) {
-      const uint32_t sl = consumed % SINK_SLOTS, ph = (consumed / SINK_SLOTS) & 1;
-      sink_mbar_wait(&my_bars[sl], ph);
-      const float4* src = reinterpret_cast<const float4*>(my_ring + sl * SLOT);
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const int idx = lane + 32 * k;
-        z[k] = (4 * idx < m) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (m & 3) {                                     // the float4 that straddles column m: its tail is row padding (any bits)
+      if (has_seg) {
+        const uint32_t sl = consumed % SLOTS, ph = (consumed / SLOTS) & 1;
+        sink_mbar_wait(&my_bars[sl], ph);
+        const float4* src = reinterpret_cast<const float4*>(my_ring + sl * C);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          const int c = 4 * (lane + 32 * k);
-          if (c < m && c + 3 >= m) {
-            if (c + 1 >= m) z[k].y = 0.f;
-            if (c + 2 >= m) z[k].z = 0.f;
-            z[k].w = 0.f;
+          const int idx = lane + 32 * k;
+          z[k] = (c0 + 4 * idx < m) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (m & 3) {                                   // the float4 that straddles column m: its tail is row padding (any bits)
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            const int c = c0 + 4 * (lane + 32 * k);
+            if (c < m && c + 3 >= m) {
+              if (c + 1 >= m) z[k].y = 0.f;
+              if (c + 2 >= m) z[k].z = 0.f;
+              z[k].w = 0.f;
+            }
           }
         }
-      }
-      ++consumed;
-      __syncwarp();                                    // every lane has its part of the row in registers
-      const int nxt = row + SINK_SLOTS * SINK_WARPS;
-      if (lane == 0 && nxt < r1_real) {
-        sink_row_copy(my_ring + sl * SLOT, Sb + (int64_t)nxt * a.lds, row_bytes, &my_bars[sl]);
-        ++issued;
-      }
-      if (!unit_reg) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
-          z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
+        ++consumed;
+        __syncwarp();                                  // every lane has its part of the row in registers
+        const int nxt = row + SLOTS * G;
+        if (lane == 0 && nxt < r1_real) {
+          sink_row_copy(my_ring + sl * C, Sb + (int64_t)nxt * a.lds + c0, seg_bytes, &my_bars[sl]);
+          ++issued;
         }
+        if (!unit_reg) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
+            z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);     // masked through v = -inf
       }
     } else {                                           // the dustbin row is the constant dustbin score
 #pragma unroll
@@ -161,41 +178,57 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
   };
 
   prefetch_first();
+  uint32_t rowpar = 0;                                 // parity of the exchange buffer (alternates per row of the group)
   for (int it = 0; it < a.iters; ++it) {
     float4 cacc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     float cacc_m = 0.f;
-    const float v_m = v_s[VD];
+    const float v_m = v_s[MC];
 
-    for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
+    for (int row = r0 + grp; row < r1; row += G) {
       float4 z[V];
       take_row(row, z);
-      // t = z + v, masked; row max
-      const float t_m = dz + v_m;                    // dustbin column entry of this row
-      float mx = t_m;
+      // t = z + v, masked; maximum over this warp's segment (the dustbin column entry belongs to segment 0)
+      const float t_m = dz + v_m;
+      float mx = (sub == 0) ? t_m : -CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const int c = 4 * (lane + 32 * k);
+        const int c = c0 + 4 * (lane + 32 * k);
         const float4 vv = *reinterpret_cast<const float4*>(v_s + c);   // columns >= m: finite z + (-inf) = -inf, e = 0
         z[k].x += vv.x; z[k].y += vv.y; z[k].z += vv.z; z[k].w += vv.w;
         mx = fmaxf(mx, fmaxf(fmaxf(z[k].x, z[k].y), fmaxf(z[k].z, z[k].w)));
       }
       mx = warp_max(mx);
+      const float mxs = (mx == -CUDART_INF_F) ? 0.f : mx;               // an all-padding segment: e = 2^-inf = 0, not NaN
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        z[k].x = ex2_approx((z[k].x - mx) * LOG2E_F);
-        z[k].y = ex2_approx((z[k].y - mx) * LOG2E_F);
-        z[k].z = ex2_approx((z[k].z - mx) * LOG2E_F);
-        z[k].w = ex2_approx((z[k].w - mx) * LOG2E_F);
+        z[k].x = ex2_approx((z[k].x - mxs) * LOG2E_F);
+        z[k].y = ex2_approx((z[k].y - mxs) * LOG2E_F);
+        z[k].z = ex2_approx((z[k].z - mxs) * LOG2E_F);
+        z[k].w = ex2_approx((z[k].w - mxs) * LOG2E_F);
         sum += (z[k].x + z[k].y) + (z[k].z + z[k].w);
       }
-      const float e_m = ex2_approx((t_m - mx) * LOG2E_F);
-      const float s_i = warp_sum(sum) + e_m;
-      const float w_i = __fdiv_rn((row < n) ? a_reg : a_last, s_i);
-      if (it == a.iters - 1 && lane == 0)
-        a.u[(int64_t)b * (n + 1) + row] = ((row < n) ? a.norm : a.log_a_last) - (mx + logf(s_i));
+      const float e_m = (sub == 0) ? ex2_approx((t_m - mxs) * LOG2E_F) : 0.f;
+      float s_i = warp_sum(sum) + e_m;
+      float mxg = mx, f_w = 1.f;
+      if (W > 1) {                                     // combine the segments of the row: S = sum_w S_w 2^(mx_w - mx)
+        float2* x = xr + (rowpar * G + grp) * W;
+        if (lane == 0) x[sub] = make_float2(mx, s_i);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(W * 32) : "memory");
+        float2 p[W];
+#pragma unroll
+        for (int w2 = 0; w2 < W; ++w2) { p[w2] = x[w2]; mxg = fmaxf(mxg, p[w2].x); }
+        s_i = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < W; ++w2) s_i = fmaf(p[w2].y, ex2_approx((p[w2].x - mxg) * LOG2E_F), s_i);   // fixed order: identical in every warp
+        f_w = ex2_approx((mx - mxg) * LOG2E_F);
+        rowpar ^= 1u;
+      }
+      const float w_i = __fdiv_rn((row < n) ? a_reg : a_last, s_i) * f_w;
+      if (it == a.iters - 1 && sub == 0 && lane == 0)
+        a.u[(int64_t)b * (n + 1) + row] = ((row < n) ? a.norm : a.log_a_last) - (mxg + logf(s_i));
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         cacc[k].x = fmaf(z[k].x, w_i, cacc[k].x); cacc[k].y = fmaf(z[k].y, w_i, cacc[k].y);
@@ -204,21 +237,21 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
       cacc_m = fmaf(e_m, w_i, cacc_m);
     }
     prefetch_first();                                 // next sweep's (or the final pass's) first rows fly during the reduction
-    // warp -> CTA
-    float* myred = red + warp * a.mpad;
+    // warp -> CTA: a row group's warps own disjoint column segments of red[grp]
+    float* myred = red + grp * a.mpad;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const int c = 4 * (lane + 32 * k);
+      const int c = c0 + 4 * (lane + 32 * k);
       if (c < m) *reinterpret_cast<float4*>(myred + c) = cacc[k];       // entries >= m are zero
     }
     __syncthreads();                                  // (a) all float4 column sums are in `red`
-    if (lane == 0) myred[m] = cacc_m;                 // column m = dustbin column (may overlap a float4 tail)
+    if (sub == 0 && lane == 0) myred[m] = cacc_m;     // column m = dustbin column (may overlap a float4 tail)
     __syncthreads();
     float* part = a.partial + ((int64_t)(it & 1) * a.B * a.SP + (int64_t)b * a.SP + strip) * a.mpad;
     for (int j = tid; j <= m; j += blockDim.x) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < SINK_WARPS; ++w) s += red[w * a.mpad + j];
+      for (int w = 0; w < G; ++w) s += red[w * a.mpad + j];
       part[j] = s;
     }
     // only the SP CTAs of this pair exchange data: a per-pair barrier (own 128-byte line) lets the pairs drift apart,
@@ -239,7 +272,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
       for (int e = 0; e < 4; ++e) {
         const int j = 4 * j4 + e;
         if (j < m) v_s[j] = a.norm + v_s[j] - logf(cc[e]);
-        else if (j == m) v_s[VD] = a.log_b_last + v_s[VD] - logf(cc[e]);
+        else if (j == m) v_s[MC] = a.log_b_last + v_s[MC] - logf(cc[e]);
       }
     }
     __syncthreads();
@@ -247,19 +280,19 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
 
   // final pass: scores = Z + u + v - norm   (optimal_transport.py:28, superglue.py:111)
   {
-    const float v_m = v_s[VD];
-    for (int row = r0 + warp; row < r1; row += SINK_WARPS) {
+    const float v_m = v_s[MC];
+    for (int row = r0 + grp; row < r1; row += G) {
       float4 z[V];
       take_row(row, z);
       float u_i = 0.f;
       if (a.iters > 0) {
-        if (lane == 0) u_i = a.u[(int64_t)b * (n + 1) + row];
+        if (lane == 0) u_i = __ldcg(a.u + (int64_t)b * (n + 1) + row);
         u_i = __shfl_sync(0xffffffffu, u_i, 0);
       }
       float* out = a.scores + ((int64_t)b * (n + 1) + row) * (m + 1);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const int c = 4 * (lane + 32 * k);
+        const int c = c0 + 4 * (lane + 32 * k);
         if (c < m) {
           const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
           if (c + 0 < m) out[c + 0] = (z[k].x + u_i) + vv.x - a.norm;
@@ -268,52 +301,62 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, 1) sinkhorn_kernel(SinkArgs a
           if (c + 3 < m) out[c + 3] = (z[k].w + u_i) + vv.w - a.norm;
         }
       }
-      if (lane == 0) out[m] = (dz + u_i) + v_m - a.norm;
+      if (sub == 0 && lane == 0) out[m] = (dz + u_i) + v_m - a.norm;
     }
   }
 }
 
-struct SinkPlan { int V, SP, rows_per_strip, mpad, pairs_per_launch; size_t smem; };
+struct SinkPlan { int V, W, slots, occ, SP, rows_per_strip, mpad, pairs_per_launch; size_t smem; };
+constexpr int SINK_MAX_COLS = 8192;
+
+template <int V, int W, int SLOTS>
+inline size_t sinkhorn_smem(int mpad) {
+  constexpr int C = 128 * V, G = SINK_WARPS / W;
+  return ((size_t)(W * C + 4) + (size_t)G * mpad + (size_t)SINK_WARPS * SLOTS * C) * sizeof(float) +
+         (size_t)SINK_WARPS * SLOTS * sizeof(uint64_t) + (size_t)2 * G * W * sizeof(float2) + 128;
+}
 
 inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
-  if (m <= 512) p->V = 4; else if (m <= 1024) p->V = 8; else if (m <= 2048) p->V = 16;
-  else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > 2048 columns not supported (swap the images)", m);
+  p->mpad = (int)align_up(m + 1, 4);
+  if (m <= 512)       { p->V = 4;  p->W = 1; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 1, 2>(p->mpad); }
+  else if (m <= 1024) { p->V = 4;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 2, 2>(p->mpad); }
+  else if (m <= 2048) { p->V = 8;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<8, 2, 2>(p->mpad); }
+  else if (m <= 4096) { p->V = 16; p->W = 2; p->slots = 2; p->occ = 1; p->smem = sinkhorn_smem<16, 2, 2>(p->mpad); }
+  else if (m <= SINK_MAX_COLS) { p->V = 16; p->W = 4; p->slots = 1; p->occ = 1; p->smem = sinkhorn_smem<16, 4, 1>(p->mpad); }
+  else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > %d columns not supported (swap the images)", m, SINK_MAX_COLS);
+  static const int env_occ = [] { const char* e = getenv("OG_SINK_OCC"); return e ? atoi(e) : 0; }();      // experiment: force 1 CTA / SM
+  if (env_occ == 1) p->occ = 1;
   const int sms = device_info().ok ? device_info().sm_count : 148;
-  p->pairs_per_launch = std::min(B < sms ? B : sms, (int)(SINK_BARRIER_BYTES / 128));
+  const int slots_total = sms * p->occ;                 // co-resident CTAs of the cooperative launch
+  p->pairs_per_launch = std::min(B < slots_total ? B : slots_total, (int)(SINK_BARRIER_BYTES / 128));
   // experiment knobs: OG_SINK_PAIRS = pairs per launch (L2 blocking), OG_SINK_SP = max strips per pair
   static const int env_pairs = [] { const char* e = getenv("OG_SINK_PAIRS"); return e ? atoi(e) : 0; }();
-  static const int env_sp = [] { const char* e = getenv("OG_SINK_SP"); return e ? atoi(e) : 16; }();
+  static const int env_sp = [] { const char* e = getenv("OG_SINK_SP"); return e ? atoi(e) : 32; }();
   if (env_pairs > 0 && env_pairs < p->pairs_per_launch) p->pairs_per_launch = env_pairs;
-  int sp = sms / p->pairs_per_launch;
+  int sp = slots_total / p->pairs_per_launch;
   if (sp > env_sp) sp = env_sp;
-  const int max_sp = cdiv(n + 1, SINK_WARPS);
+  const int max_sp = cdiv(n + 1, SINK_WARPS / p->W);
   if (sp > max_sp) sp = max_sp;
   if (sp < 1) sp = 1;
   p->SP = sp;
   p->rows_per_strip = cdiv(n + 1, sp);
-  p->mpad = (int)align_up(m + 1, 4);
-  if (p->mpad < 128 * p->V) {                      // v_s is read as float4 up to column 128 V - 1
-    // only columns < m are ever used, but the smem reads must stay in bounds
-  }
-  p->smem = ((size_t)(128 * p->V + 4) + (size_t)SINK_WARPS * (size_t)std::max(p->mpad, 128 * p->V) + (size_t)SINK_WARPS * SINK_SLOTS * 128 * p->V) * sizeof(float) +
-            (size_t)SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128;
   return OG_OK;
 }
 
 inline int64_t sinkhorn_workspace_bytes(int B, int n, int m) {
   SinkPlan p;
   if (sinkhorn_plan(B, n, m, &p) != OG_OK) return -1;
-  const int64_t mp = std::max(p.mpad, 128 * p.V);
-  return SINK_BARRIER_BYTES + align_up((int64_t)B * (n + 1) * 4, 256) + align_up(2LL * B * p.SP * mp * 4, 256);
+  // sized for the largest strip count any occupancy setting may choose (the plan depends on the device only through the SM count)
+  const int64_t sp_max = std::max(p.SP, 32);
+  return SINK_BARRIER_BYTES + align_up((int64_t)B * (n + 1) * 4, 256) + align_up(2LL * B * sp_max * p.mpad * 4, 256);
 }
 
-template <int V>
+template <int V, int W, int SLOTS>
 inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream) {
   static DeviceFlags attr_set;
-  if (attr_set.once()) {                       // largest request of this instantiation: m = 128 V  =>  mpad = 128 V + 4
-    OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(((1 + SINK_WARPS) * (128 * V + 4) + SINK_WARPS * SINK_SLOTS * 128 * V) * sizeof(float) +
-                                       SINK_WARPS * SINK_SLOTS * sizeof(uint64_t) + 128)));
+  if (attr_set.once()) {                 // largest request of this instantiation: m = 128 V W
+    OG_CUDA(cudaFuncSetAttribute(sinkhorn_kernel<V, W, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sinkhorn_smem<V, W, SLOTS>(128 * V * W + 4)));
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.B * a.SP);
@@ -324,7 +367,7 @@ inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream)
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, sinkhorn_kernel<V>, a));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, sinkhorn_kernel<V, W, SLOTS>, a));
   launch_counter()++;
   return OG_OK;
 }
@@ -337,7 +380,6 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
   if (ws_bytes < sinkhorn_workspace_bytes(B, n, m)) return fail(OG_EWORKSPACE, "sinkhorn: workspace too small");
   if (lds % 4 != 0 || lds < m || (reinterpret_cast<uintptr_t>(S) & 15) || strideS % 4 != 0)
     return fail(OG_EINVAL, "sinkhorn: S rows must be 16-byte aligned (lds %% 4 == 0, lds >= m)");
-  const int64_t mp = std::max(p.mpad, 128 * p.V);
   char* w = static_cast<char*>(ws);
   unsigned int* barrier = reinterpret_cast<unsigned int*>(w); w += SINK_BARRIER_BYTES;
   float* u = reinterpret_cast<float*>(w); w += align_up((int64_t)B * (n + 1) * 4, 256);
@@ -354,13 +396,13 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
     a.norm = norm; a.log_a_last = log_a_last; a.log_b_last = log_b_last;
     a.scores = scores + (int64_t)b0 * (n + 1) * (m + 1);
     a.u = u; a.partial = partial; a.barrier = barrier;
-    a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = (int)mp;
+    a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = p.mpad;
     OG_CUDA(cudaMemsetAsync(barrier, 0, (size_t)nb * 128, stream));
-    switch (p.V) {
-      case 4:  rc = sinkhorn_launch_v<4>(a, p, stream); break;
-      case 8:  rc = sinkhorn_launch_v<8>(a, p, stream); break;
-      default: rc = sinkhorn_launch_v<16>(a, p, stream); break;
-    }
+    if (p.V == 4 && p.W == 1)       rc = sinkhorn_launch_v<4, 1, 2>(a, p, stream);
+    else if (p.V == 4)              rc = sinkhorn_launch_v<4, 2, 2>(a, p, stream);
+    else if (p.V == 8)              rc = sinkhorn_launch_v<8, 2, 2>(a, p, stream);
+    else if (p.W == 2)              rc = sinkhorn_launch_v<16, 2, 2>(a, p, stream);
+    else                            rc = sinkhorn_launch_v<16, 4, 1>(a, p, stream);
     if (rc != OG_OK) return rc;
   }
   return OG_OK;

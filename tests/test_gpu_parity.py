@@ -320,7 +320,9 @@ def test_attention_operator(B, H, dh, nq, nk):
 
 @pytest.mark.parametrize('B,n,m,iters,reg,scale', [(2, 30, 41, 50, 1.0, 3.0), (1, 513, 512, 20, 1.0, 10.0),
                                                    (3, 100, 1025, 10, 0.7, 2.0), (1, 2048, 2048, 100, 1.0, 8.0),
-                                                   (20, 64, 64, 30, 1.0, 5.0), (1, 4, 2048, 3, 1.0, 1.0)])
+                                                   (20, 64, 64, 30, 1.0, 5.0), (1, 4, 2048, 3, 1.0, 1.0),
+                                                   (1, 300, 3000, 15, 1.0, 3.0), (2, 1500, 4100, 10, 0.8, 4.0), (1, 64, 8192, 5, 1.0, 2.0),
+                                                   (3, 700, 513, 25, 1.0, 6.0), (1, 2048, 1030, 40, 1.0, 8.0)])
 def test_sinkhorn_operator(B, n, m, iters, reg, scale):
     g = torch.Generator().manual_seed(5)
     S = scale * torch.randn(B, n, m, generator=g)

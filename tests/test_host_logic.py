@@ -43,7 +43,8 @@ def test_argument_validation_without_gpu():
     assert lib.og_packed_weight_floats(bad) < 0
     assert lib.og_superglue_forward(cfg, None, None, None, 1, 8, 8, None, None, None, None, None, None, None, None, None, None,
                                     None, None, None, None, None, 0, None) == -1     # OG_EINVAL, no CUDA call made
-    assert lib.og_workspace_bytes(cfg, 2, 100, 3000) < 0                             # > 2048 columns: unsupported
+    assert lib.og_workspace_bytes(cfg, 2, 100, 3000) > 0                             # wide rows: several warps share a row
+    assert lib.og_workspace_bytes(cfg, 2, 100, 9000) < 0 and b'8192' in lib.og_last_error()   # the documented limit
 
 
 def test_state_dict_contract_matches_reference_layout(golden):
