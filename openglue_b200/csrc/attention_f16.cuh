@@ -169,9 +169,11 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
       for (int iloc = 0; iloc < nblk; ++iloc, ++it) {
         const int i = it;
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
+        OG_TRACE_EVT(0, i);
         mbar_wait(&bars->k_full[s], ph);
         if (i >= 2) mbar_wait(&bars->p_full[j], ((i - 2) >> 1) & 1);     // the softmax has read S_{i-2} out of this buffer
         tc_fence_after();
+        OG_TRACE_EVT(1, i);
         if (elect_one()) {
           const uint32_t khi = smem_u32(sK + s * k_stage_bytes<CG>()), klo = khi + K_HALF;
           const uint32_t d_s = tmem + COL_SP + 128 * j;
@@ -193,10 +195,13 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
       const int ntot = nblk * ((a.ntiles - t_first + t_stride - 1) / t_stride);
       for (int i = 0; i < ntot; ++i) {
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1, jph = (i >> 1) & 1;
+        OG_TRACE_EVT(2, i);
         mbar_wait(&bars->v_full[s], ph);
         mbar_wait(&bars->p_full[j], jph);
+        OG_TRACE_EVT(3, i);
         mbar_wait(&bars->o_empty[j], jph ^ 1);
         tc_fence_after();
+        OG_TRACE_EVT(4, i);
         if (elect_one()) {
           const uint32_t vhi = smem_u32(sV + s * v_stage_bytes<CG>()), vlo = vhi + V_HALF;
           const uint32_t p_hi = tmem + COL_SP + 128 * j + 64, p_lo = p_hi + 32;
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
       for (int c = 0; c < 32; ++c) acc[c] = fmaf(acc[c], corr, __uint_as_float(o[c]));
       tc_fence_before();
       arrive_leader(&bars->o_empty[j]);
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(7, i);
     };
 
 #pragma unroll 1
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
       const int kbase = iloc * BNK + 32 * g;
       mbar_wait(&bars->s_full[j], jph);
       tc_fence_after();
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(5, i);
       if (iloc == nblk - 1 && t + t_stride < a.ntiles) {
         mbar_wait(&bars->q_free, nt & 1);
         tc_fence_after();
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
       xch[(j * 2 + g) * 128 + trow] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");   // also: BOTH warpgroups have read S_i (nothing below touches S)
       mx = fmaxf(mx, xch[(j * 2 + (g ^ 1)) * 128 + trow]);
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(8, i);
       const float m_new = fmaxf(m_run, mx);
       const float mc = fmaf(m_new, c1, -P_SHIFT);      // p = 2^(s c1 - mc) = 2^14 exp(scale (s - m))
       const float corr = ex2_approx(mc_run - mc);
@@ -352,11 +360,13 @@ __global__ void __launch_bounds__(tcaf::THREADS, 1) attention_f16_kernel(const _
 #pragma unroll
         for (int w = 0; w < 16; ++w) { hi[w] = __byte_perm(hi[w], 0, 0x1032); lo[w] = __byte_perm(lo[w], 0, 0x1032); }
       }
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(9, i);
       tmem_st_32x16(sp + 64 + 16 * g, hi);             // P_hi: keys [32g, 32g+32) = packed columns [16g, 16g+16)
       tmem_st_32x16(sp + 96 + 16 * g, lo);             // (this thread has waited for P.V_{i-2} in fold_o(i-2))
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->p_full[j]);
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(6, i);
       l_run = fmaf(l_run, corr, r0 + r1);
       m_run = m_new; mc_run = mc;
       if (iloc >= 1) fold_o(i - 1, corr_prev);

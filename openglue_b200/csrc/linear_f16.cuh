@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&bars->empty[s], ph ^ 1);
+          OG_TRACE_EVT(0, it);
           uint8_t* dst = smem + s * STAGE_BYTES;
           const int k = kb * BK;
           mbar_arrive_expect_tx(&bars->a_land[s], A_BYTES);    // columns beyond K arrive as zeros (TMA out-of-bounds fill)
@@ -185,8 +186,10 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&bars->acc_empty[buf], gph ^ 1);
         mbar_wait(&bars->b_full[s], ph);
+        OG_TRACE_EVT(3, it);
         mbar_wait(&bars->a_full[s], ph);
         tc_fence_after();
+        OG_TRACE_EVT(4, it);
         if (elect_one()) {
           const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + A_BYTES), blo = bhi + B_TILE;
           const uint32_t d = tmem + buf * 128;
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
       for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&bars->a_land[s], ph);
+        if (warp == 8 && lane == 0) OG_TRACE_EVT(1, it);
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         tmem_wait_st();
         tc_fence_before();
         arrive_leader(&bars->a_full[s]);
+        if (warp == 8 && lane == 0) OG_TRACE_EVT(2, it);
       }
     }
   } else {
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_full[buf], gph);
         tc_fence_after();
+        if (warp == 0 && lane == 0) OG_TRACE_EVT(5, g);
 #pragma unroll
         for (int ch = 0; ch < HN / 32; ++ch) {
           uint32_t v[32];
@@ -289,8 +295,10 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         }
         tc_fence_before();
         arrive_leader(&bars->acc_empty[buf]);
+        if (warp == 0 && lane == 0) OG_TRACE_EVT(6, g);
       }
       // ---- epilogue for this tile (overlaps the next tile's first chunks)
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(8, ntile);
       const int grow = m0 + trow;
       const bool row_ok = grow < a.rows;
       if (wg_tid == 0 && !r_tma && OUTK != 3) tma_store_wait_read<0>();   // the previous tile's stores have read the staging buffers
@@ -370,6 +378,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
           }
         }
       }
+      if (warp == 0 && lane == 0) OG_TRACE_EVT(9, ntile);
     }
     if (OUTK == 1 && a.amax_out) {
       tmax = warp_max(tmax);
