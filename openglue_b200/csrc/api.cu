@@ -8,6 +8,7 @@
 #include "attention_tc.cuh"
 #include "linear_f16.cuh"
 #include "attention_f16.cuh"
+#include "attention_f16t.cuh"
 #include "sinkhorn.cuh"
 #include "match.cuh"
 #include "gt_matches.cuh"
@@ -519,7 +520,7 @@ static int forward_impl(const og_config* cfg, const float* Wp, const float* Whi,
     TcAttnArgs a{w.q + (int64_t)qrow0 * d, d, (int64_t)nq * d, w.o + (int64_t)qrow0 * d, d, (int64_t)nq * d,
                  batch, nq, nk, H, d, (float)pow((double)dh, -0.5)};
     F16AttnScales sc{ss.q, ss.k, ss.v, ss.o, 0};
-    return attention_f16_launch(a, sc, kh16 + (int64_t)krow0 * d, kl16 + (int64_t)krow0 * d, d, vth16 + voff, vtl16 + voff, ldv, dh, st);
+    return attention_f16_dispatch(a, sc, kh16 + (int64_t)krow0 * d, kl16 + (int64_t)krow0 * d, d, vth16 + voff, vtl16 + voff, ldv, dh, st);
   };
   auto mlp_f16 = [&](int l, int row0, int rows, float* ax0, float* ax1, float* ao, float** sx_new) -> int {
     float* sh = new_slot();
@@ -744,8 +745,8 @@ int og_attention_f16_fwd(const float* q, int64_t ldq, int64_t strideq, const flo
     return fail(OG_EUNSUPPORTED, "attention_f16: head_dim 64 and 16-byte aligned rows required");
   TcAttnArgs a{q, ldq, strideq, out, ldo, strideo, batch, nq, nk, num_heads, num_heads * head_dim, (float)pow((double)head_dim, -0.5)};
   F16AttnScales sc{q_amax, k_scale, v_scale, out_amax, swap_halves};
-  return attention_f16_launch(a, sc, static_cast<const __half*>(khi), static_cast<const __half*>(klo), ldk,
-                              static_cast<const __half*>(vthi), static_cast<const __half*>(vtlo), ldvt, head_dim, (cudaStream_t)stream);
+  return attention_f16_dispatch(a, sc, static_cast<const __half*>(khi), static_cast<const __half*>(klo), ldk,
+                                static_cast<const __half*>(vthi), static_cast<const __half*>(vtlo), ldvt, head_dim, (cudaStream_t)stream);
 }
 
 }  // extern "C"
