@@ -238,6 +238,22 @@ int og_sinkhorn_fwd(const float* S, int64_t lds, int64_t strideS, const float* d
                     int batch, int n, int m, int iters, float reg,
                     float* scores, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Training form of the Sinkhorn operator.  og_sinkhorn_train_fwd = og_sinkhorn_fwd that also
+ * records the scaling vectors of every iteration (hist: og_sinkhorn_hist_floats floats: u [B][T][n+1], v [B][T+1][m+1]);
+ * og_sinkhorn_bwd = the gradient through all T unrolled iterations, as torch autograd computes it for the reference's
+ * get_matching_probs / log_otp_solver in training_step (matching_module.py:99-105):
+ *   dscores [B,n+1,m+1] = d loss / d scores (dense)  ->  dS_aug [B,n+1,m+1] = d loss / d S_aug (its [:n,:m] block is
+ *   d loss / d S of the score GEMM, reg included) and ddustbin[0] = d loss / d dustbin_score.  Deterministic.        */
+int64_t og_sinkhorn_hist_floats(int batch, int n, int m, int iters);
+int og_sinkhorn_train_fwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin,
+                          int batch, int n, int m, int iters, float reg, float* scores, float* hist,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int64_t og_sinkhorn_bwd_workspace_bytes(int batch, int n, int m, int iters);
+int og_sinkhorn_bwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin,
+                    int batch, int n, int m, int iters, float reg, const float* hist,
+                    const float* dscores, float* dS_aug, float* ddustbin,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Mutual-argmax match extraction on scores[:, :n, :m].  Replaces
  * models/matching_module.py:174-187 and inference.py:176-190 (ties -> lowest index).
  *   workspace >= og_match_workspace_bytes(B, n, m)                                             */

@@ -78,6 +78,10 @@ SYMBOLS = {
     'og_attention_tc_fwd': (_I, [_P, _L, _L, _P, _P, _L, _P, _P, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P]),
     'og_sinkhorn_workspace_bytes': (_L, [_I, _I, _I]),
     'og_sinkhorn_fwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _L, _P]),
+    'og_sinkhorn_hist_floats': (_L, [_I, _I, _I, _I]),
+    'og_sinkhorn_train_fwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _P, _L, _P]),
+    'og_sinkhorn_bwd_workspace_bytes': (_L, [_I, _I, _I, _I]),
+    'og_sinkhorn_bwd': (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
     'og_match_workspace_bytes': (_L, [_I, _I, _I]),
     'og_match_fwd': (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
     'og_gt_matches_workspace_bytes': (_L, [_I, _I, _I]),

@@ -10,6 +10,7 @@
 #include "attention_f16.cuh"
 #include "attention_f16t.cuh"
 #include "sinkhorn.cuh"
+#include "sinkhorn_bwd.cuh"
 #include "match.cuh"
 #include "gt_matches.cuh"
 #include "criterion.cuh"
@@ -303,6 +304,31 @@ int og_sinkhorn_fwd(const float* S, int64_t lds, int64_t strideS, const float* d
   OG_CHECK_ARG(batch > 0 && n > 0 && m > 0 && iters >= 0 && reg > 0.f, "sinkhorn: bad sizes");
   return sinkhorn_launch(S, lds, strideS, dustbin, batch, n, m, iters, reg, scores, workspace, workspace_bytes,
                          (cudaStream_t)stream);
+}
+
+int64_t og_sinkhorn_hist_floats(int batch, int n, int m, int iters) {
+  return (batch > 0 && n > 0 && m > 0 && iters >= 0) ? sinkhorn_hist_floats(batch, n, m, iters) : -1;
+}
+
+int og_sinkhorn_train_fwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin, int batch, int n, int m,
+                          int iters, float reg, float* scores, float* hist, void* workspace, int64_t workspace_bytes, void* stream) {
+  OG_CHECK_ARG(S && dustbin && scores && workspace && hist, "sinkhorn_train_fwd: null pointer");
+  OG_CHECK_ARG(batch > 0 && n > 0 && m > 0 && iters >= 0 && reg > 0.f, "sinkhorn_train_fwd: bad sizes");
+  return sinkhorn_launch(S, lds, strideS, dustbin, batch, n, m, iters, reg, scores, workspace, workspace_bytes, (cudaStream_t)stream,
+                         hist, hist + (int64_t)batch * iters * (n + 1));
+}
+
+int64_t og_sinkhorn_bwd_workspace_bytes(int batch, int n, int m, int iters) {
+  return (batch > 0 && n > 0 && m > 0 && iters >= 0) ? sinkhorn_bwd_workspace_bytes(batch, n, m, iters) : -1;
+}
+
+int og_sinkhorn_bwd(const float* S, int64_t lds, int64_t strideS, const float* dustbin, int batch, int n, int m, int iters, float reg,
+                    const float* hist, const float* dscores, float* dS_aug, float* ddustbin, void* workspace, int64_t workspace_bytes,
+                    void* stream) {
+  OG_CHECK_ARG(S && dustbin && hist && dscores && dS_aug && ddustbin && workspace, "sinkhorn_bwd: null pointer");
+  OG_CHECK_ARG(batch > 0 && n > 0 && m > 0 && iters >= 0 && reg > 0.f, "sinkhorn_bwd: bad sizes");
+  return sinkhorn_bwd_launch(S, lds, strideS, dustbin, batch, n, m, iters, reg, hist, dscores, dS_aug, ddustbin, workspace,
+                             workspace_bytes, (cudaStream_t)stream);
 }
 
 int64_t og_match_workspace_bytes(int batch, int n, int m) { return match_workspace_bytes(batch, n, m); }

@@ -29,7 +29,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int COL_QHI = 0, COL_QLO = 32, COL_SP = 64, COL_O = 320;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SHIFT = 14.f;
-constexpr int REGS_SOFTMAX = 120, REGS_PRODUCER = 32;        // 512 x 120 + 128 x 32 = 65536
+constexpr int REGS_SOFTMAX = 104, REGS_PRODUCER = 64;        // setmaxnreg moves registers INSIDE the CTA's launch allocation:
+                                                             // 512 x 104 + 128 x 64 = 61440 = 640 threads x 96 registers (checked by the launcher)
 
 struct __align__(16) Barriers {
   uint64_t k_full[MAX_STAGES], k_empty[MAX_STAGES], v_full[MAX_STAGES], v_empty[MAX_STAGES];
@@ -353,6 +354,10 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       const float corr = ex2_approx(mc_run - mc);
       const unsigned long long nmc2 = pack2(-mc, -mc);
       unsigned long long rs2 = 0ull;
+      if (prev >= 0) {                                 // P_i goes where P_prev sits: the team's previous P.V must have read it
+        mbar_wait(bar_of, (prev >> 1) & 1);            // (issued a block and a half ago: no wait in steady state; folded below)
+        tc_fence_after();
+      }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {                 // two halves of 16 columns: P leaves the registers as soon as it is split
         uint32_t hi[8], lo[8];
@@ -458,6 +463,15 @@ inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   static DeviceFlags attr_set;
   if (attr_set.once()) {
     OG_CUDA(cudaFuncSetAttribute(attention_f16t_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<CG>()));
+  }
+  {  // the register hand-over only works if the compiled register count gives the CTA the pool the two setmaxnreg values add up to
+    static int regs_ok = -1;
+    if (regs_ok < 0) {
+      cudaFuncAttributes fa;
+      OG_CUDA(cudaFuncGetAttributes(&fa, attention_f16t_kernel<CG>));
+      regs_ok = (fa.numRegs * THREADS >= 512 * REGS_SOFTMAX + 128 * REGS_PRODUCER) ? 1 : 0;
+    }
+    if (!regs_ok) return fail(OG_EUNSUPPORTED, "attention_f16t: register pool too small for the setmaxnreg split (rebuild)");
   }
   TcAttnArgs ap = a;
   ap.nqg = cdiv(cdiv(a.nq, BM), CG);

@@ -57,6 +57,8 @@ constexpr int COL_A = 256;
 constexpr int OUT_TILE = 128 * 128;       // one staging tile: [128 rows x 32 fp32] or [128 rows x 64 fp16] (128-byte rows)
 constexpr int OUT_BYTES = 2 * 2 * OUT_TILE;
 constexpr int MAX_STAGES = 3;
+constexpr int CHUNK_KB = 2;               // K blocks per accumulator chunk: K = 128 = 8 k-steps x 3 MMAs = 24 accumulations into TMEM,
+                                          // the same count (and therefore the same truncation error) as the tf32 form's K = 64 chunks
 
 template <int PAIR> struct Cfg {
   static constexpr int STAGES = PAIR ? 3 : 2;
@@ -72,7 +74,7 @@ struct __align__(16) Barriers {
   uint32_t tmem_base;
   alignas(16) float bias[2][BN];
 };
-struct Sched { int ntmg, ntn, ngroups, nkb; };
+struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };
 }  // namespace tcf
 
 template <int PAIR, int RTMA, int OUTK>
@@ -179,39 +181,44 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
   } else if (warp == 13 && crank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only when paired)
     const uint32_t idesc = make_idesc_f16(BM * NC, BN);
-    int it = 0;                                                // k-block counter = chunk counter (one K block per chunk)
+    int it = 0, g = 0;                                         // k-block and chunk counters
     for (int t = g_first; t < sc.ngroups; t += g_stride) {
-      for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
-        const int buf = it & 1, gph = (it >> 1) & 1;
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
+      for (int c = 0; c < sc.nchunks; ++c, ++g) {
+        const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_empty[buf], gph ^ 1);
-        mbar_wait(&bars->b_full[s], ph);
-        OG_TRACE_EVT(3, it);
-        mbar_wait(&bars->a_full[s], ph);
         tc_fence_after();
-        OG_TRACE_EVT(4, it);
-        if (elect_one()) {
-          const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + A_BYTES), blo = bhi + B_TILE;
-          const uint32_t d = tmem + buf * 128;
+        const int kb_end = min((c + 1) * CHUNK_KB, sc.nkb);
+        for (int kb = c * CHUNK_KB; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&bars->b_full[s], ph);
+          OG_TRACE_EVT(3, it);
+          mbar_wait(&bars->a_full[s], ph);
+          tc_fence_after();
+          OG_TRACE_EVT(4, it);
+          if (elect_one()) {
+            const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + A_BYTES), blo = bhi + B_TILE;
+            const uint32_t d = tmem + buf * 128;
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t dbhi = make_sdesc_sw128(bhi + kk * 32), dblo = make_sdesc_sw128(blo + kk * 32);
-            const uint32_t ahi = tmem + COL_A + s * 64 + kk * 8, alo = ahi + 32;
-            if (PAIR) {
-              umma_f16_ts_pair(d, alo, dbhi, idesc, kk ? 1u : 0u);
-              umma_f16_ts_pair(d, ahi, dblo, idesc, 1u);
-              umma_f16_ts_pair(d, ahi, dbhi, idesc, 1u);
-            } else {
-              umma_f16_ts(d, alo, dbhi, idesc, kk ? 1u : 0u);
-              umma_f16_ts(d, ahi, dblo, idesc, 1u);
-              umma_f16_ts(d, ahi, dbhi, idesc, 1u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t dbhi = make_sdesc_sw128(bhi + kk * 32), dblo = make_sdesc_sw128(blo + kk * 32);
+              const uint32_t ahi = tmem + COL_A + s * 64 + kk * 8, alo = ahi + 32;
+              const uint32_t acc0 = (kb > c * CHUNK_KB || kk) ? 1u : 0u;
+              if (PAIR) {
+                umma_f16_ts_pair(d, alo, dbhi, idesc, acc0);
+                umma_f16_ts_pair(d, ahi, dblo, idesc, 1u);
+                umma_f16_ts_pair(d, ahi, dbhi, idesc, 1u);
+              } else {
+                umma_f16_ts(d, alo, dbhi, idesc, acc0);
+                umma_f16_ts(d, ahi, dblo, idesc, 1u);
+                umma_f16_ts(d, ahi, dbhi, idesc, 1u);
+              }
             }
+            commit(&bars->empty[s]);
+            commit(&bars->a_empty[s]);
+            if (kb == kb_end - 1) commit(&bars->acc_full[buf]);
           }
-          commit(&bars->empty[s]);
-          commit(&bars->a_empty[s]);
-          commit(&bars->acc_full[buf]);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         tma_load_3d(s_out + (half * 2 + 0) * OUT_TILE, &map_r, &bars->r_full[half], n0 + half * HN, m0, bz);
         tma_load_3d(s_out + (half * 2 + 1) * OUT_TILE, &map_r, &bars->r_full[half], n0 + half * HN + 32, m0, bz);
       }
-      for (int kb = 0; kb < sc.nkb; ++kb, ++g) {
+      for (int c = 0; c < sc.nchunks; ++c, ++g) {
         const int buf = g & 1, gph = (g >> 1) & 1;
         mbar_wait(&bars->acc_full[buf], gph);
         tc_fence_after();
@@ -440,7 +447,7 @@ inline int linear_f16_launch_t(const F16LinearArgs& a, const __half* Bh, const _
   const Kern kern = a.Y ? (r_tma ? kerns[1] : kerns[0]) : (a.Yh ? kerns[2] : kerns[3]);
   Sched sc;
   sc.ntmg = cdiv(cdiv(a.rows, BM), NC); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
-  sc.nkb = cdiv(K, BK);
+  sc.nkb = cdiv(K, BK); sc.nchunks = cdiv(sc.nkb, CHUNK_KB);
   const int sms = device_info().ok ? device_info().sm_count : 148;
   const int nclusters = std::min(sc.ngroups, sms / NC);
   cudaLaunchConfig_t cfg = {};

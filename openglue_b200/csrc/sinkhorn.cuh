@@ -37,6 +37,8 @@ struct SinkArgs {
   float* partial;                        // [2, B, SP, mpad] workspace
   unsigned int* barrier;                 // [B] counters, one per pair, 128 bytes apart; zeroed before launch
   int SP, rows_per_strip, mpad;
+  float* hist_u;                         // optional [B][iters][n+1]: u_t of every iteration  (kept for the backward pass,
+  float* hist_v;                         // optional [B][iters+1][m+1]: v_t, row 0 = v_0 = 0   csrc/sinkhorn_bwd.cuh)
 };
 
 constexpr int SINK_WARPS = 8;
@@ -227,8 +229,11 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
         rowpar ^= 1u;
       }
       const float w_i = __fdiv_rn((row < n) ? a_reg : a_last, s_i) * f_w;
-      if (it == a.iters - 1 && sub == 0 && lane == 0)
-        a.u[(int64_t)b * (n + 1) + row] = ((row < n) ? a.norm : a.log_a_last) - (mxg + logf(s_i));
+      if ((it == a.iters - 1 || a.hist_u) && sub == 0 && lane == 0) {
+        const float u_i = ((row < n) ? a.norm : a.log_a_last) - (mxg + logf(s_i));
+        if (it == a.iters - 1) a.u[(int64_t)b * (n + 1) + row] = u_i;
+        if (a.hist_u) a.hist_u[((int64_t)b * a.iters + it) * (n + 1) + row] = u_i;
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         cacc[k].x = fmaf(z[k].x, w_i, cacc[k].x); cacc[k].y = fmaf(z[k].y, w_i, cacc[k].y);
@@ -276,6 +281,10 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
       }
     }
     __syncthreads();
+    if (a.hist_v && strip == 0) {                     // every CTA of the pair holds the same v: one of them records it
+      float* hv = a.hist_v + ((int64_t)b * (a.iters + 1) + it + 1) * (m + 1);
+      for (int j = tid; j <= m; j += blockDim.x) hv[j] = (j < m) ? v_s[j] : v_s[MC];
+    }
   }
 
   // final pass: scores = Z + u + v - norm   (optimal_transport.py:28, superglue.py:111)
@@ -316,16 +325,8 @@ inline size_t sinkhorn_smem(int mpad) {
          (size_t)SINK_WARPS * SLOTS * sizeof(uint64_t) + (size_t)2 * G * W * sizeof(float2) + 128;
 }
 
-inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
-  p->mpad = (int)align_up(m + 1, 4);
-  if (m <= 512)       { p->V = 4;  p->W = 1; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 1, 2>(p->mpad); }
-  else if (m <= 1024) { p->V = 4;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 2, 2>(p->mpad); }
-  else if (m <= 2048) { p->V = 8;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<8, 2, 2>(p->mpad); }
-  else if (m <= 4096) { p->V = 16; p->W = 2; p->slots = 2; p->occ = 1; p->smem = sinkhorn_smem<16, 2, 2>(p->mpad); }
-  else if (m <= SINK_MAX_COLS) { p->V = 16; p->W = 4; p->slots = 1; p->occ = 1; p->smem = sinkhorn_smem<16, 4, 1>(p->mpad); }
-  else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > %d columns not supported (swap the images)", m, SINK_MAX_COLS);
-  static const int env_occ = [] { const char* e = getenv("OG_SINK_OCC"); return e ? atoi(e) : 0; }();      // experiment: force 1 CTA / SM
-  if (env_occ == 1) p->occ = 1;
+// strips per pair / pairs per cooperative launch for p->occ co-resident CTAs per SM
+inline void sinkhorn_decompose(SinkPlan* p, int B, int n) {
   const int sms = device_info().ok ? device_info().sm_count : 148;
   const int slots_total = sms * p->occ;                 // co-resident CTAs of the cooperative launch
   p->pairs_per_launch = std::min(B < slots_total ? B : slots_total, (int)(SINK_BARRIER_BYTES / 128));
@@ -340,6 +341,26 @@ inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
   if (sp < 1) sp = 1;
   p->SP = sp;
   p->rows_per_strip = cdiv(n + 1, sp);
+}
+
+inline int sinkhorn_plan(int B, int n, int m, SinkPlan* p) {
+  p->mpad = (int)align_up(m + 1, 4);
+  if (m <= 512)       { p->V = 4;  p->W = 1; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 1, 2>(p->mpad); }
+  else if (m <= 1024) { p->V = 4;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<4, 2, 2>(p->mpad); }
+  else if (m <= 2048) { p->V = 8;  p->W = 2; p->slots = 2; p->occ = 2; p->smem = sinkhorn_smem<8, 2, 2>(p->mpad); }
+  else if (m <= 4096) { p->V = 16; p->W = 2; p->slots = 2; p->occ = 1; p->smem = sinkhorn_smem<16, 2, 2>(p->mpad); }
+  else if (m <= SINK_MAX_COLS) { p->V = 16; p->W = 4; p->slots = 1; p->occ = 1; p->smem = sinkhorn_smem<16, 4, 1>(p->mpad); }
+  else return fail(OG_EUNSUPPORTED, "sinkhorn: m = %d > %d columns not supported (swap the images)", m, SINK_MAX_COLS);
+  static const int env_occ = [] { const char* e = getenv("OG_SINK_OCC"); return e ? atoi(e) : 0; }();      // experiment: force 1 CTA / SM
+  // experiment: OG_SINK_CFG=VWS picks another instantiation for 1024 < m <= 2048 (824 = V 8, W 2, 4 slots; 1612; 444)
+  static const int env_cfg = [] { const char* e = getenv("OG_SINK_CFG"); return e ? atoi(e) : 0; }();
+  if (m > 1024 && m <= 2048) {
+    if (env_cfg == 824)  { p->V = 8;  p->W = 2; p->slots = 4; p->occ = 1; p->smem = sinkhorn_smem<8, 2, 4>(p->mpad); }
+    if (env_cfg == 1612) { p->V = 16; p->W = 1; p->slots = 2; p->occ = 1; p->smem = sinkhorn_smem<16, 1, 2>(p->mpad); }
+    if (env_cfg == 444)  { p->V = 4;  p->W = 4; p->slots = 4; p->occ = 2; p->smem = sinkhorn_smem<4, 4, 4>(p->mpad); }
+  }
+  if (env_occ == 1) p->occ = 1;
+  sinkhorn_decompose(p, B, n);
   return OG_OK;
 }
 
@@ -373,7 +394,8 @@ inline int sinkhorn_launch_v(SinkArgs a, const SinkPlan& p, cudaStream_t stream)
 }
 
 inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const float* dustbin, int B, int n, int m,
-                           int iters, float reg, float* scores, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+                           int iters, float reg, float* scores, void* ws, int64_t ws_bytes, cudaStream_t stream,
+                           float* hist_u = nullptr, float* hist_v = nullptr) {
   SinkPlan p;
   int rc = sinkhorn_plan(B, n, m, &p);
   if (rc != OG_OK) return rc;
@@ -388,6 +410,7 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
   const float norm = -logf((float)(n + m));
   const float log_a_last = norm + (float)log((double)m);     // log_a[-1] += math.log(n_cols)
   const float log_b_last = norm + (float)log((double)n);     // log_b[-1] += math.log(n_rows)
+  if (hist_v) OG_CUDA(cudaMemsetAsync(hist_v, 0, (size_t)B * (iters + 1) * (m + 1) * sizeof(float), stream));   // row 0 of every pair = v_0 = 0
   for (int b0 = 0; b0 < B; b0 += p.pairs_per_launch) {
     const int nb = std::min(p.pairs_per_launch, B - b0);
     SinkArgs a;
@@ -397,8 +420,13 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
     a.scores = scores + (int64_t)b0 * (n + 1) * (m + 1);
     a.u = u; a.partial = partial; a.barrier = barrier;
     a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = p.mpad;
+    a.hist_u = hist_u ? hist_u + (int64_t)b0 * iters * (n + 1) : nullptr;
+    a.hist_v = hist_v ? hist_v + (int64_t)b0 * (iters + 1) * (m + 1) : nullptr;
     OG_CUDA(cudaMemsetAsync(barrier, 0, (size_t)nb * 128, stream));
-    if (p.V == 4 && p.W == 1)       rc = sinkhorn_launch_v<4, 1, 2>(a, p, stream);
+    if (p.V == 8 && p.slots == 4)   rc = sinkhorn_launch_v<8, 2, 4>(a, p, stream);
+    else if (p.V == 16 && p.W == 1) rc = sinkhorn_launch_v<16, 1, 2>(a, p, stream);
+    else if (p.V == 4 && p.W == 4)  rc = sinkhorn_launch_v<4, 4, 4>(a, p, stream);
+    else if (p.V == 4 && p.W == 1)  rc = sinkhorn_launch_v<4, 1, 2>(a, p, stream);
     else if (p.V == 4)              rc = sinkhorn_launch_v<4, 2, 2>(a, p, stream);
     else if (p.V == 8)              rc = sinkhorn_launch_v<8, 2, 2>(a, p, stream);
     else if (p.W == 2)              rc = sinkhorn_launch_v<16, 2, 2>(a, p, stream);

@@ -198,6 +198,24 @@ def test_forward_matches_oracle(batch, n, m, kw, family, precision):
     assert (res['matching_scores1'].cpu()[dec1] - ref['matching_scores1'][dec1]).abs().max() <= bound
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'fp16x3'])
+def test_no_descriptors_option(precision):
+    """config['no_descriptors'] (reference superglue.py:45-49): the GNN starts from the positional encoding alone; the residual
+    mix (:59-62) still blends the raw descriptors in."""
+    cfg = default_config(descriptor_dim=256, num_stages=2, num_iters=20)
+    cfg['no_descriptors'] = True
+    sd = synthetic_state_dict(cfg, seed=4)
+    data = synthetic_pairs(2, 150, 131, 256, 1, family='planted', seed=9)
+    ref64 = O.run(sd, cfg, data, 0.2, dtype=torch.float64)
+    ref = O.run(sd, cfg, data, 0.2)
+    with_desc = O.run(sd, {**cfg, 'no_descriptors': False}, data, 0.2)
+    assert (with_desc['scores'] - ref['scores']).abs().max() > 1e-2          # the option changes the answer
+    bound = max(TOL, 2 * float((ref['scores'].double() - ref64['scores']).abs().max()))
+    res = MatchingCore(_model(cfg, sd, precision), 0.2)(_to_dev(data), want_scores=True)
+    assert (res['scores'].cpu().double() - ref64['scores']).abs().max() <= bound
+    check_matches(res, ref, ref64['scores'], bound)
+
+
 def test_host_buffers_roundtrip(golden):
     """MatchingCore with HOST tensors (the e2e path of bench.py): same answer as device tensors."""
     fx = golden('tiny_planted')
