@@ -314,7 +314,7 @@ def main():
     stats = torch.zeros(3, device=dev, dtype=torch.float64)
     loss_acc = torch.zeros(2, device=dev)
 
-    from openglue_b200.sharding import match_statistics
+    from openglue_b200.sharding import all_reduce_loss, match_statistics
     with_loss = args.workload == 'C4'          # BASELINE.json configs[3]: reference criterion on every rank + NCCL loss all-reduce
     side = torch.cuda.Stream(dev)              # the collective runs beside the next step's kernels, never on the compute stream
     if with_loss:
@@ -329,9 +329,11 @@ def main():
         """sum over ranks of a small device tensor, on the side stream (self.log(..., sync_dist=True), matching_module.py:102-103)"""
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            if dist is not None:
+            if out is loss_acc:
+                all_reduce_loss(t)                     # mean over ranks (sharding.py)
+            elif dist is not None:
                 dist.all_reduce(t)
-            out.copy_(t / world if out is loss_acc else t)
+            out.copy_(t)
         t.record_stream(side)
 
     def step(inputs):

@@ -9,6 +9,7 @@
 #include "linear_f16.cuh"
 #include "attention_f16.cuh"
 #include "attention_f16t.cuh"
+#include "attention_f16p.cuh"
 #include "sinkhorn.cuh"
 #include "sinkhorn_bwd.cuh"
 #include "match.cuh"

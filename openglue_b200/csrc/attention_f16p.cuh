@@ -1,37 +1,39 @@
-// fp16 hi/lo fused attention, "two teams" form: the production kernel of OG_PREC_FP16X3.
+// fp16 hi/lo fused attention, "ping-pong" form: the production kernel of OG_PREC_FP16X3.
 //
 // Same arithmetic, operands and TMEM layout as csrc/attention_f16.cuh; what changes is who does the softmax.  With fp16
-// operands a key block costs the tensor pipe 768 cycles (24 MMAs), but ONE group of softmax warps needs ~1650 cycles per
-// block for its serial chain (S load -> row max exchange -> 32 exponentials + hi/lo split -> P store -> fold of O_{i-1};
-// event trace profiles/r02_trace_attention_f16_v1.txt) - the tensor pipe idled half of the time.  Here TWO teams of two
-// softmax warpgroups work on ALTERNATE key blocks: team e owns every block with (global index & 1) == e together with the
-// S/P/O TMEM buffers e, keeps its own online-softmax state (row max, row sum, 32 output channels per thread) and the two
-// partial results of a tile are merged once, at the end of the tile, through shared memory:
+// operands a key block costs the tensor pipe 768 cycles (24 MMAs), but the column-split softmax needs ~1650 cycles per block:
+// its two warpgroups are phase-locked by the row-max exchange, so both sit in the exponential phase at the same time (the
+// MUFU unit then paces them: 512 cycles per block) and both leave it idle during their load / store / fold phases (event
+// trace profiles/r02_trace_attention_f16_v1.txt).  Here the two softmax warpgroups work on ALTERNATE key blocks: warpgroup e
+// owns every block with (global index & 1) == e together with the S/P/O TMEM buffers e; a thread owns a whole 64-column logit
+// row (no exchange, no barrier inside the block loop), keeps its own online-softmax state (row max, row sum, all 64 output
+// channels) and the two partial results of a tile are merged once, at the end of the tile, through shared memory:
 //     out = (acc_0 2^(m_0 - m) + acc_1 2^(m_1 - m)) / (l_0 2^(m_0 - m) + l_1 2^(m_1 - m)),   m = max(m_0, m_1)
-// Within a team the two warpgroups split a block by columns exactly as before (half-row maxima through shared memory and
-// one 256-thread named barrier).  The element-wise chain uses the packed fp32x2 instructions (FFMA2 / FADD2): one issue
-// slot for two logits.  20 warps: 0-7 team 0, 8-15 team 1, 16 TMA, 17 QK^T issue + TMEM, 18 P.V issue; setmaxnreg moves the
-// producer warps' registers to the softmax warpgroups.
+// One warpgroup's exponentials overlap the other's TMEM traffic.  The element-wise chain uses the packed fp32x2
+// instructions (FFMA2 / FADD2); setmaxnreg moves the producer warps' registers to the softmax warpgroups so that nothing
+// spills (a 16-warp, two-teams variant whose accumulators spilled ran at HALF the speed:
+// profiles/r02_trace_attention_f16_two_teams_16warps.txt, csrc/attention_f16t.cuh).
+// 12 warps: 0-3 warpgroup 0, 4-7 warpgroup 1, 8 TMA, 9 QK^T issue + TMEM, 10 P.V issue.
 #pragma once
 #include "tc_common.cuh"
-#include "attention_f16.cuh"     // F16AttnScales, TcAttnArgs
+#include "attention_f16t.cuh"    // packed fp32x2 helpers, F16AttnScales, TcAttnArgs
 #include <math_constants.h>
 #include <stdlib.h>
 #include <algorithm>
 
 namespace og {
-namespace tcat {
-constexpr int BM = 128, BNK = 64, DH = 64, HD = 32;
+namespace tcap {
+using tcat::pack2; using tcat::unpack2; using tcat::ffma2; using tcat::fadd2; using tcat::fsub2;
+constexpr int BM = 128, BNK = 64, DH = 64, HD = 32;      // HD: output channels a warpgroup finalises
 constexpr int MAX_STAGES = 4;
-template <int CG> __host__ __device__ constexpr int stages() { return CG == 2 ? 4 : 2; }      // CG = 1 stages whole K / V tiles: 32 KB per stage
-constexpr int THREADS = 640;
+template <int CG> __host__ __device__ constexpr int stages() { return CG == 2 ? 4 : 2; }
+constexpr int THREADS = 384;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_QHI = 0, COL_QLO = 32, COL_SP = 64, COL_O = 320;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SHIFT = 14.f;
-constexpr int REGS_SOFTMAX = 104, REGS_PRODUCER = 64;        // setmaxnreg moves registers INSIDE the CTA's launch allocation:
-                                                             // 512 x 104 + 128 x 64 = 61440 = 640 threads x 96 registers (checked by the launcher)
-
+constexpr int REGS_SOFTMAX = 216, REGS_PRODUCER = 72;    // setmaxnreg moves registers INSIDE the CTA's launch allocation:
+                                                         // 256 x 216 + 128 x 72 = 64512 = 384 threads x 168 registers (checked by the launcher)
 struct __align__(16) Barriers {
   uint64_t k_full[MAX_STAGES], k_empty[MAX_STAGES], v_full[MAX_STAGES], v_empty[MAX_STAGES];
   uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2];
@@ -39,50 +41,34 @@ struct __align__(16) Barriers {
 };
 template <int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * 128; }
 template <int CG> __host__ __device__ constexpr int v_stage_bytes() { return 2 * (DH / CG) * 128; }
-constexpr int XCH_FLOATS = 2 * 2 * 2 * 128;                  // [team][block parity][warpgroup][row] half-row maxima
-constexpr int LM_FLOATS = 2 * 2 * 2 * 128 * 2;               // [tile parity][team][warpgroup][row] (mc, l)
+constexpr int LM_FLOATS = 2 * 2 * 128 * 2;               // [tile parity][warpgroup][row] (mc, l)
 constexpr int MRG_STRIDE = HD + 1;
-constexpr int MRG_FLOATS = 2 * 2 * 128 * MRG_STRIDE;         // [tile parity][warpgroup][row][33] team 1's partial output
-constexpr int QST_FLOATS = 16 * 32 * HD;                     // per softmax warp a [32 rows x 32 channels] staging tile (Q in, O out)
+constexpr int MRG_FLOATS = 2 * 2 * 128 * MRG_STRIDE;     // [tile parity][warpgroup][row][33]: the 32 channels the OTHER warpgroup finalises
+constexpr int QST_FLOATS = 8 * 32 * DH;                  // per softmax warp a [32 rows x 64 channels] staging tile (Q in, O out)
 template <int CG> __host__ __device__ constexpr int smem_bytes() {
-  return 1024 + stages<CG>() * (k_stage_bytes<CG>() + v_stage_bytes<CG>()) + 512 + (XCH_FLOATS + LM_FLOATS + MRG_FLOATS + QST_FLOATS) * 4;
+  return 1024 + stages<CG>() * (k_stage_bytes<CG>() + v_stage_bytes<CG>()) + 512 + (LM_FLOATS + MRG_FLOATS + QST_FLOATS) * 4;
 }
-
-__device__ __forceinline__ unsigned long long pack2(float x, float y) {
-  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ unsigned long long fsub2(unsigned long long a, unsigned long long b) {
-  unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-}  // namespace tcat
+}  // namespace tcap
 
 template <int CG>
-__global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const __grid_constant__ CUtensorMap map_khi,
+__global__ void __launch_bounds__(tcap::THREADS, 1) attention_f16p_kernel(const __grid_constant__ CUtensorMap map_khi,
                                                                           const __grid_constant__ CUtensorMap map_klo,
                                                                           const __grid_constant__ CUtensorMap map_vhi,
                                                                           const __grid_constant__ CUtensorMap map_vlo,
                                                                           TcAttnArgs a, F16AttnScales sc) {
-  using namespace tcat;
+  using namespace tcap;
   using namespace tc;
   constexpr int KROWS = BNK / CG, VCH = DH / CG;
   constexpr int K_HALF = KROWS * 128, V_HALF = VCH * 128;
   constexpr int STAGES = stages<CG>();
 
   launch_dependents();
-  extern __shared__ uint8_t og_tcat_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcat_smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ uint8_t og_tcap_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcap_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + STAGES * k_stage_bytes<CG>();
   Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<CG>());
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
-  float* lm = xch + XCH_FLOATS;
+  float* lm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   float* mrg = lm + LM_FLOATS;
   float* qst_all = mrg + MRG_FLOATS;
 
@@ -107,18 +93,18 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       mbar_init(&bars->k_full[i], 1); mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
-    mbar_init(&bars->q_ready, 8 * CG);               // the eight warps of the team that hands a tile's Q over (in both CTAs)
+    mbar_init(&bars->q_ready, 4 * CG);               // the four warps of the warpgroup that hands a tile's Q over (in both CTAs)
     mbar_init(&bars->q_free, 1);
-    for (int j = 0; j < 2; ++j) {                    // buffer j belongs to team j: eight warps per CTA
-      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 8 * CG);
-      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG);
+    for (int j = 0; j < 2; ++j) {                    // buffer j belongs to warpgroup j: four warps per CTA
+      mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 4 * CG);
+      mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 4 * CG);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
     prefetch_tensormap(&map_vhi); prefetch_tensormap(&map_vlo);
   }
   if (CG == 2) cluster_sync_all();
-  if (warp == 17) { if (CG == 2) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base); else tmem_alloc<TMEM_COLS>(&bars->tmem_base); }
+  if (warp == 9) { if (CG == 2) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base); else tmem_alloc<TMEM_COLS>(&bars->tmem_base); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -130,9 +116,9 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
   };
   auto commit = [&](uint64_t* bar) { if (CG == 2) umma_commit_pair(bar); else umma_commit(bar); };
 
-  if (warp >= 16) {
+  if (warp >= 8) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-  if (warp == 16) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;
@@ -168,14 +154,14 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       }
       }
     }
-  } else if ((warp == 17 || warp == 18) && crank == 0) {
+  } else if ((warp == 9 || warp == 10) && crank == 0) {
     // ------------------------------------------------------------------ MMA issuers (leader CTA only when paired)
     const uint32_t idesc_qk = make_idesc_f16(BM * CG, BNK);
     const uint32_t idesc_pv = make_idesc_f16(BM * CG, DH);
     auto mma = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t id, uint32_t acc) {
       if (CG == 2) umma_f16_ts_pair(d, at, bd, id, acc); else umma_f16_ts(d, at, bd, id, acc);
     };
-    if (warp == 17) {
+    if (warp == 9) {
       int it = 0, nt = 0;
       for (int t = t_first; t < a.ntiles; t += t_stride, ++nt) {
       mbar_wait_t(&bars->q_ready, nt & 1);
@@ -184,7 +170,7 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
         OG_TRACE_EVT(0, i);
         mbar_wait_t(&bars->k_full[s], ph);
-        if (i >= 2) mbar_wait_t(&bars->p_full[j], ((i - 2) >> 1) & 1);     // team j has read S_{i-2} out of its buffer
+        if (i >= 2) mbar_wait_t(&bars->p_full[j], ((i - 2) >> 1) & 1);     // warpgroup j has read S_{i-2} out of its buffer
         tc_fence_after();
         OG_TRACE_EVT(1, i);
         if (elect_one()) {
@@ -234,55 +220,54 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
     }
   }
   } else {
-    // ------------------------------------------------------------------ softmax teams
+    // ------------------------------------------------------------------ softmax warpgroups (ping-pong over key blocks)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
-    const int team = warp >> 3;                      // owns key blocks with (global index & 1) == team and the TMEM buffers `team`
-    const int g = (warp >> 2) & 1;                   // column half inside the team: logit columns / output channels [32g, 32g+32)
+    const int team = warp >> 2;                      // owns key blocks with (global index & 1) == team and the TMEM buffers `team`
     const int qd = warp & 3;
     const int trow = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    float* xch_t = xch + team * (2 * 2 * 128);
     const float s_q = f16_scale_for(__ldcg(sc.q_amax));
     const float s_k = __ldcg(sc.k_scale), s_v = __ldcg(sc.v_scale);
     const float c1 = a.scale * LOG2E / (s_q * s_k);
     const unsigned long long c1_2 = pack2(c1, c1);
     const float inv_sv = 1.f / s_v;
     float omax = 0.f;
-    constexpr int LPR = HD / 4, RPI = 32 / LPR;      // 8 lanes fetch one row's 128 bytes
-    float* qst = qst_all + warp * (32 * HD);         // this warp's staging tile [32][32] (16-byte chunks XOR-swizzled by row)
+    float* qst = qst_all + warp * (32 * DH);         // this warp's staging tile [32 rows][64 ch] (16-byte chunks XOR-swizzled by row)
     const uint32_t sp = tmem + lane_base + COL_SP + 128 * team;
-    const uint32_t o_addr = tmem + lane_base + COL_O + 64 * team + g * HD;
+    const uint32_t o_addr = tmem + lane_base + COL_O + 64 * team;
     uint64_t* const bar_s = &bars->s_full[team];
     uint64_t* const bar_p = &bars->p_full[team];
     uint64_t* const bar_of = &bars->o_full[team];
     uint64_t* const bar_oe = &bars->o_empty[team];
-    const int bar_id = 1 + team;
 
-    auto load_q = [&](const TilePos& p) {            // cp.async: lands during the tile
-      const int r_in = lane / LPR, ch = lane % LPR;
+    auto load_q = [&](const TilePos& p) {            // cp.async: 16 lanes fetch one row's 256 bytes; lands during the tile
+      const int r_in = lane >> 4, ch = lane & 15;
 #pragma unroll
-      for (int k = 0; k < LPR; ++k) {
-        const int row = k * RPI + r_in, grow = tile_q0(p) + qd * 32 + row;
-        float* dst = qst + row * HD + ((ch ^ (row & (LPR - 1))) * 4);
-        const float* src = a.q + (int64_t)p.b * a.strideq + (int64_t)grow * a.ldq + p.h * DH + g * HD + ch * 4;
+      for (int k = 0; k < 16; ++k) {
+        const int row = 2 * k + r_in, grow = tile_q0(p) + qd * 32 + row;
+        float* dst = qst + row * DH + ((ch ^ (row & 15)) * 4);
+        const float* src = a.q + (int64_t)p.b * a.strideq + (int64_t)grow * a.ldq + p.h * DH + ch * 4;
         if (grow < a.nq) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto write_q = [&]() {                           // staged Q row -> scale, split, pack -> TMEM
+    auto write_q = [&]() {                           // staged Q row -> scale, split, pack -> TMEM (32 packed columns hi, 32 lo)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(qst + lane * HD + ((c ^ (lane & (LPR - 1))) * 4));
-        split_f16x2(v.x * s_q, v.y * s_q, hi[2 * c], lo[2 * c]);
-        split_f16x2(v.z * s_q, v.w * s_q, hi[2 * c + 1], lo[2 * c + 1]);
+      for (int hq = 0; hq < 2; ++hq) {               // two halves of 32 channels
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(qst + lane * DH + (((8 * hq + c) ^ (lane & 15)) * 4));
+          split_f16x2(v.x * s_q, v.y * s_q, hi[2 * c], lo[2 * c]);
+          split_f16x2(v.z * s_q, v.w * s_q, hi[2 * c + 1], lo[2 * c + 1]);
+        }
+        tmem_st_32x16(tmem + lane_base + COL_QHI + 16 * hq, hi);
+        tmem_st_32x16(tmem + lane_base + COL_QLO + 16 * hq, lo);
       }
       __syncwarp();
-      tmem_st_32x16(tmem + lane_base + COL_QHI + g * 16, hi);
-      tmem_st_32x16(tmem + lane_base + COL_QLO + g * 16, lo);
       tmem_wait_st();
       tc_fence_before();
       arrive_leader(&bars->q_ready);
@@ -297,26 +282,30 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
     const int grow = tile_q0(tp) + trow;
     tp = tile_next(tp);
     const bool has_next = t + t_stride < a.ntiles;
-    // the team that owns the tile's LAST key block sees the last QK^T retire first: it hands the next tile's Q over
+    // the warpgroup that owns the tile's LAST key block sees the last QK^T retire first: it hands the next tile's Q over
     const bool writer_next = has_next && (((it0 + nblk - 1) & 1) == team);
     if (nt == 0 && team == 0) write_q();
     if (writer_next) load_q(tp);
 
-    unsigned long long acc2[HD / 2];
+    unsigned long long acc2[DH / 2];                 // all 64 output channels of this warpgroup's key blocks
 #pragma unroll
-    for (int c = 0; c < HD / 2; ++c) acc2[c] = 0ull;
+    for (int c = 0; c < DH / 2; ++c) acc2[c] = 0ull;
     float m_run = -CUDART_INF_F, mc_run = -CUDART_INF_F, l_run = 0.f, corr_prev = 0.f;
     int prev = -1;
 
-    auto fold_o = [&](int i, float corr) {           // acc = acc * corr + my channels of O_i
+    auto fold_o = [&](int i, float corr) {           // acc = acc * corr + O_i
       mbar_wait_t(bar_of, (i >> 1) & 1);
       tc_fence_after();
-      uint32_t o[32];
-      tmem_ld_32x32(o_addr, o);
-      tmem_wait_ld();
       const unsigned long long corr2 = pack2(corr, corr);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc2[c] = ffma2(acc2[c], corr2, pack2(__uint_as_float(o[2 * c]), __uint_as_float(o[2 * c + 1])));
+      for (int hq = 0; hq < 2; ++hq) {
+        uint32_t o[32];
+        tmem_ld_32x32(o_addr + 32 * hq, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          acc2[16 * hq + c] = ffma2(acc2[16 * hq + c], corr2, pack2(__uint_as_float(o[2 * c]), __uint_as_float(o[2 * c + 1])));
+      }
       tc_fence_before();
       arrive_leader(bar_oe);
       if (warp == 0 && lane == 0) OG_TRACE_EVT(7, i);
@@ -325,9 +314,8 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
 #pragma unroll 1
     for (int iloc = (team - it0) & 1; iloc < nblk; iloc += 2) {
       const int i = it0 + iloc;
-      const int par = (i >> 1) & 1;
-      const int kbase = iloc * BNK + 32 * g;
-      mbar_wait_t(bar_s, par);
+      const int kbase = iloc * BNK;
+      mbar_wait_t(bar_s, (i >> 1) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) OG_TRACE_EVT(5, i);
       if (iloc == nblk - 1 && writer_next) {         // the tile's last QK^T has retired: the next tile's Q goes in now
@@ -335,36 +323,39 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
         tc_fence_after();
         write_q();
       }
-      uint32_t s[32];
-      tmem_ld_32x32(sp + 32 * g, s);
+      uint32_t s0[32], s1[32];                         // logit columns [0,32) and [32,64) of my row
+      tmem_ld_32x32(sp, s0);
+      tmem_ld_32x32(sp + 32, s1);
       tmem_wait_ld();
-      if (kbase + 32 > a.nk) {
+      if (kbase + BNK > a.nk) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) if (kbase + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
+        for (int c = 0; c < 32; ++c) {
+          if (kbase + c >= a.nk) s0[c] = __float_as_uint(-CUDART_INF_F);
+          if (kbase + 32 + c >= a.nk) s1[c] = __float_as_uint(-CUDART_INF_F);
+        }
       }
-      float mx = -CUDART_INF_F;
+      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
-      xch_t[(par * 2 + g) * 128 + trow] = mx;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, xch_t[(par * 2 + (g ^ 1)) * 128 + trow]);
+      for (int c = 0; c < 32; c += 2) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[c]), __uint_as_float(s0[c + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[c]), __uint_as_float(s1[c + 1])));
+      }
       if (warp == 0 && lane == 0) OG_TRACE_EVT(8, i);
-      const float m_new = fmaxf(m_run, mx);
-      const float mc = fmaf(m_new, c1, -P_SHIFT);
+      const float m_new = fmaxf(m_run, fmaxf(mx0, mx1));
+      const float mc = fmaf(m_new, c1, -P_SHIFT);      // p = 2^(s c1 - mc) = 2^14 exp(scale (s - m))
       const float corr = ex2_approx(mc_run - mc);
       const unsigned long long nmc2 = pack2(-mc, -mc);
       unsigned long long rs2 = 0ull;
-      if (prev >= 0) {                                 // P_i goes where P_prev sits: the team's previous P.V must have read it
+      if (prev >= 0) {                                 // P_i goes where P_prev sits: this warpgroup's previous P.V must have read it
         mbar_wait_t(bar_of, (prev >> 1) & 1);            // (issued a block and a half ago: no wait in steady state; folded below)
         tc_fence_after();
       }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {                 // two halves of 16 columns: P leaves the registers as soon as it is split
+      auto quarter = [&](const uint32_t (&sv)[32], int off, int hh) {   // 16 columns: exponentials, hi/lo split, P store
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
           float t0, t1;
-          unpack2(ffma2(pack2(__uint_as_float(s[16 * hh + c]), __uint_as_float(s[16 * hh + c + 1])), c1_2, nmc2), t0, t1);
+          unpack2(ffma2(pack2(__uint_as_float(sv[off + c]), __uint_as_float(sv[off + c + 1])), c1_2, nmc2), t0, t1);
           const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
           const unsigned long long p2 = pack2(p0, p1);
           rs2 = fadd2(rs2, p2);
@@ -376,9 +367,10 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
           hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh2);
           lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
         }
-        tmem_st_32x8(sp + 64 + 16 * g + 8 * hh, hi);   // P_hi: keys [32g + 16hh, +16) = packed columns [16g + 8hh, +8)
-        tmem_st_32x8(sp + 96 + 16 * g + 8 * hh, lo);   // (this thread has waited for the team's previous P.V in fold_o)
-      }
+        tmem_st_32x8(sp + 64 + 8 * hh, hi);            // P_hi: keys [16 hh, +16) = packed columns [8 hh, +8)
+        tmem_st_32x8(sp + 96 + 8 * hh, lo);
+      };
+      quarter(s0, 0, 0); quarter(s0, 16, 1); quarter(s1, 0, 2); quarter(s1, 16, 3);
       if (warp == 0 && lane == 0) OG_TRACE_EVT(9, i);
       tmem_wait_st();
       tc_fence_before();
@@ -393,53 +385,51 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
     }
     if (prev >= 0) fold_o(prev, corr_prev);
 
-    // ---- merge the two teams' partial results of this tile (team 1 -> shared memory -> team 0), normalise, store
+    // ---- merge the two warpgroups' partial results of this tile: warpgroup e finalises channels [32 e, 32 e + 32)
     const int tp2 = nt & 1;
-    float* lm_t = lm + tp2 * (2 * 2 * 128 * 2);
-    reinterpret_cast<float2*>(lm_t)[(team * 2 + g) * 128 + trow] = make_float2(mc_run, l_run);
-    if (team == 1) {
-      float* mr = mrg + ((tp2 * 2 + g) * 128 + trow) * MRG_STRIDE;
+    reinterpret_cast<float2*>(lm)[(tp2 * 2 + team) * 128 + trow] = make_float2(mc_run, l_run);
+    {
+      float* mr = mrg + ((tp2 * 2 + team) * 128 + trow) * MRG_STRIDE;      // my contribution to the channels the other one finalises
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { float x, y; unpack2(acc2[c], x, y); mr[2 * c] = x; mr[2 * c + 1] = y; }
+      for (int c = 0; c < 16; ++c) { float x, y; unpack2(acc2[16 * (team ^ 1) + c], x, y); mr[2 * c] = x; mr[2 * c + 1] = y; }
     }
-    asm volatile("bar.sync 3, 512;" ::: "memory");
-    if (team == 0) {
-      const float2* lmv = reinterpret_cast<const float2*>(lm_t);
-      const float2 a0 = lmv[(0 * 2 + (g ^ 1)) * 128 + trow], b0 = lmv[(1 * 2 + 0) * 128 + trow], b1 = lmv[(1 * 2 + 1) * 128 + trow];
-      const float mc0 = mc_run, mc1 = b0.x;            // the two warpgroups of a team share their running maximum
-      const float mcf = fmaxf(mc0, mc1);
-      const float f0 = ex2_approx(mc0 - mcf), f1 = ex2_approx(mc1 - mcf);     // a team without blocks: 2^(-inf) = 0
-      const float l_tot = fmaf(l_run + a0.y, f0, (b0.y + b1.y) * f1);
-      const float inv = inv_sv / l_tot;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      const float2 ot = reinterpret_cast<const float2*>(lm)[(tp2 * 2 + (team ^ 1)) * 128 + trow];
+      const float mcf = fmaxf(mc_run, ot.x);
+      const float f0 = ex2_approx(mc_run - mcf), f1 = ex2_approx(ot.x - mcf);     // a warpgroup without blocks: 2^(-inf) = 0
+      const float inv = inv_sv / fmaf(l_run, f0, ot.y * f1);
       const float w0 = f0 * inv, w1 = f1 * inv;
-      const float* mr = mrg + ((tp2 * 2 + g) * 128 + trow) * MRG_STRIDE;
+      const float* mr = mrg + ((tp2 * 2 + (team ^ 1)) * 128 + trow) * MRG_STRIDE;
       float out[HD];
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        float x, y; unpack2(acc2[c], x, y);
+        float x, y; unpack2(acc2[16 * team + c], x, y);
         out[2 * c] = fmaf(x, w0, mr[2 * c] * w1); out[2 * c + 1] = fmaf(y, w0, mr[2 * c + 1] * w1);
       }
       if (sc.out_amax && grow < a.nq) {
 #pragma unroll
         for (int c = 0; c < HD; ++c) omax = fmaxf(omax, fabsf(out[c]));
       }
-      // row-coalesced stores through this warp's staging tile (free: the next tile's Q, if this team loads it, is issued below)
+      // row-coalesced stores through this warp's staging tile (if this warpgroup loads the next tile's Q, that copy has been consumed by write_q)
+      float* ost = qst;                               // [32 rows][32 ch], 8 lanes per row
+      constexpr int LPR = HD / 4, RPI = 32 / LPR;
 #pragma unroll
       for (int c = 0; c < HD / 4; ++c)
-        *reinterpret_cast<float4*>(qst + lane * HD + ((c ^ (lane & (LPR - 1))) * 4)) = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+        *reinterpret_cast<float4*>(ost + lane * HD + ((c ^ (lane & (LPR - 1))) * 4)) = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
       __syncwarp();
       const int r_in = lane / LPR, ch = lane % LPR;
 #pragma unroll
       for (int k = 0; k < LPR; ++k) {
         const int row = k * RPI + r_in, orow_g = grow - lane + row;
         if (orow_g < a.nq)
-          *reinterpret_cast<float4*>(a.out + (int64_t)b * a.strideo + (int64_t)orow_g * a.ldo + h * DH + g * HD + ch * 4) =
-              *reinterpret_cast<const float4*>(qst + row * HD + ((ch ^ (row & (LPR - 1))) * 4));
+          *reinterpret_cast<float4*>(a.out + (int64_t)b * a.strideo + (int64_t)orow_g * a.ldo + h * DH + team * HD + ch * 4) =
+              *reinterpret_cast<const float4*>(ost + row * HD + ((ch ^ (row & (LPR - 1))) * 4));
       }
       __syncwarp();
     }
     }
-    if (sc.out_amax && team == 0) {
+    if (sc.out_amax) {
       omax = warp_max(omax);
       if (lane == 0 && omax > 0.f) atomic_amax(sc.out_amax, omax);
     }
@@ -447,13 +437,13 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
   }
   __syncthreads();
   if (CG == 2) cluster_sync_all();
-  if (warp == 17) { tc_fence_after(); if (CG == 2) tmem_dealloc_pair<tcat::TMEM_COLS>(tmem); else tmem_dealloc<tcat::TMEM_COLS>(tmem); }
+  if (warp == 9) { tc_fence_after(); if (CG == 2) tmem_dealloc_pair<tcap::TMEM_COLS>(tmem); else tmem_dealloc<tcap::TMEM_COLS>(tmem); }
 }
 
 template <int CG>
-inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
+inline int attention_f16p_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
                                    const __half* vthi, const __half* vtlo, int64_t ldvt, cudaStream_t stream) {
-  using namespace tcat;
+  using namespace tcap;
   CUtensorMap mkh, mkl, mvh, mvl;
   int rc;
   if ((rc = tc::make_tmap_2d_f16(&mkh, khi, (uint64_t)a.batch * a.nk, (uint64_t)a.d, (uint64_t)ldk, BNK / CG)) != OG_OK) return rc;
@@ -462,16 +452,16 @@ inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   if ((rc = tc::make_tmap_2d_f16(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
   static DeviceFlags attr_set;
   if (attr_set.once()) {
-    OG_CUDA(cudaFuncSetAttribute(attention_f16t_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<CG>()));
+    OG_CUDA(cudaFuncSetAttribute(attention_f16p_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<CG>()));
   }
   {  // the register hand-over only works if the compiled register count gives the CTA the pool the two setmaxnreg values add up to
     static int regs_ok = -1;
     if (regs_ok < 0) {
       cudaFuncAttributes fa;
-      OG_CUDA(cudaFuncGetAttributes(&fa, attention_f16t_kernel<CG>));
-      regs_ok = (fa.numRegs * THREADS >= 512 * REGS_SOFTMAX + 128 * REGS_PRODUCER) ? 1 : 0;
+      OG_CUDA(cudaFuncGetAttributes(&fa, attention_f16p_kernel<CG>));
+      regs_ok = (fa.numRegs * THREADS >= 256 * REGS_SOFTMAX + 128 * REGS_PRODUCER) ? 1 : 0;
     }
-    if (!regs_ok) return fail(OG_EUNSUPPORTED, "attention_f16t: register pool too small for the setmaxnreg split (rebuild)");
+    if (!regs_ok) return fail(OG_EUNSUPPORTED, "attention_f16p: register pool too small for the setmaxnreg split (rebuild)");
   }
   TcAttnArgs ap = a;
   ap.nqg = cdiv(cdiv(a.nq, BM), CG);
@@ -488,9 +478,29 @@ inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = tc::pdl_mode() ? 2 : 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_f16t_kernel<CG>, mkh, mkl, mvh, mvl, ap, sc));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_f16p_kernel<CG>, mkh, mkl, mvh, mvl, ap, sc));
   launch_counter()++;
   return OG_OK;
+}
+
+// OG_ATTN_FORM selects the softmax organisation of the fp16 attention: 2 (default) = ping-pong warpgroups (this file), 1 = two teams of
+// two warpgroups (csrc/attention_f16t.cuh, slower: spills), 0 = one team, column split (csrc/attention_f16.cuh).  All parity-tested.
+inline int& attention_f16_form() {
+  static int v = [] { const char* e = getenv("OG_ATTN_FORM"); return e ? atoi(e) : 2; }();
+  return v;
+}
+
+inline int attention_f16_dispatch(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
+                                  const __half* vthi, const __half* vtlo, int64_t ldvt, int head_dim, cudaStream_t stream) {
+  if (head_dim != 64) return fail(OG_EUNSUPPORTED, "attention_f16: head_dim %d != 64", head_dim);
+  if (!sc.q_amax || !sc.k_scale || !sc.v_scale) return fail(OG_EINVAL, "attention_f16: operand scales missing");
+  const int form = sc.swap_halves ? 0 : attention_f16_form();
+  const bool pair = attention_tc_pair_mode() != 0;
+  if (form == 2) return pair ? attention_f16p_launch_t<2>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream)
+                             : attention_f16p_launch_t<1>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  if (form == 1) return pair ? attention_f16t_launch_t<2>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream)
+                             : attention_f16t_launch_t<1>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  return attention_f16_launch(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, head_dim, stream);
 }
 
 }  // namespace og

@@ -42,3 +42,15 @@ def all_reduce_statistics(stats: torch.Tensor, group=None) -> Dict[str, float]:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     pairs, nmatch, conf = (float(x) for x in stats.tolist())
     return {'pairs': pairs, 'matches_per_pair': nmatch / max(pairs, 1.0), 'mean_confidence': conf / max(nmatch, 1.0)}
+
+
+def all_reduce_loss(loss: torch.Tensor, group=None) -> torch.Tensor:
+    """Mean over ranks of a per-rank loss vector (e.g. stack([loss, metric_loss])): what the reference's
+    ``self.log(..., sync_dist=True)`` does with the training losses (models/matching_module.py:102-103).  Each rank's
+    criterion already divides by its own pair count (utils/losses.py:51), so for equal shards this is the loss of the
+    whole batch.  In place on ``loss``' device (NCCL on GPUs, gloo on CPU); returns the reduced tensor."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        loss /= dist.get_world_size(group)
+    return loss

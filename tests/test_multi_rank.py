@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from openglue_b200.sharding import all_reduce_statistics, match_statistics, shard_pairs, shard_range
+from openglue_b200.sharding import all_reduce_loss, all_reduce_statistics, match_statistics, shard_pairs, shard_range
 from openglue_b200.synthetic import default_config, synthetic_pairs, synthetic_state_dict
 
 
@@ -68,3 +68,43 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     assert got['stats']['pairs'] == total == want['pairs']
     assert abs(got['stats']['matches_per_pair'] - want['matches_per_pair']) < 1e-9
     assert abs(got['stats']['mean_confidence'] - want['mean_confidence']) < 1e-6
+
+
+def _loss_worker(rank, world, port, total_pairs, out_path):
+    """BASELINE.json configs[3] on CPU: labels -> forward -> criterion per shard (oracles), loss reduced over the ranks."""
+    from oracle import superglue_oracle as O
+    from oracle import gt_matches_oracle as G
+    from oracle import loss_oracle as L
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    cfg = default_config(descriptor_dim=32, num_stages=1, num_iters=10)
+    sd = synthetic_state_dict(cfg, seed=0)
+    data = shard_pairs(synthetic_pairs(total_pairs, 40, 36, 32, 1, family='planted', seed=5), rank, world)
+    b = data['keypoints0'].shape[0]
+    H = torch.tensor([[0.9, 0.0, 20.0], [0.0, 0.9, 20.0], [0.0, 0.0, 1.0]]).repeat(b, 1, 1)
+    g0, g1, _ = G.gt_matches(data['keypoints0'], data['keypoints1'], {'type': ['perspective'] * b, 'H': H})
+    scores = O.run(sd, cfg, data, 0.2)['scores']
+    out = L.criterion({'gt_matches0': g0, 'gt_matches1': g1}, {'scores': scores})
+    red = all_reduce_loss(torch.stack([out['loss'], out['metric_loss']]).double())
+    if rank == 0:
+        torch.save({'loss': red}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_loss_reduction_matches_single_process(tmp_path):
+    from oracle import superglue_oracle as O
+    from oracle import gt_matches_oracle as G
+    from oracle import loss_oracle as L
+    total = 4                                            # equal shards: mean of the rank losses = loss of the whole batch
+    out = str(tmp_path / 'loss.pt')
+    mp.spawn(_loss_worker, args=(2, _free_port(), total, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)['loss']
+    cfg = default_config(descriptor_dim=32, num_stages=1, num_iters=10)
+    sd = synthetic_state_dict(cfg, seed=0)
+    data = synthetic_pairs(total, 40, 36, 32, 1, family='planted', seed=5)
+    H = torch.tensor([[0.9, 0.0, 20.0], [0.0, 0.9, 20.0], [0.0, 0.0, 1.0]]).repeat(total, 1, 1)
+    g0, g1, _ = G.gt_matches(data['keypoints0'], data['keypoints1'], {'type': ['perspective'] * total, 'H': H})
+    want = L.criterion({'gt_matches0': g0, 'gt_matches1': g1}, {'scores': O.run(sd, cfg, data, 0.2)['scores']})
+    assert abs(float(got[0]) - float(want['loss'])) < 1e-5 and float(got[1]) == 0.0
