@@ -269,7 +269,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='C3', choices=sorted(BASELINE_CONFIGS))
     ap.add_argument('--pairs-per-gpu', type=int, default=None)
-    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'tf32x3'), choices=['fp32', 'tf32x3', 'fp16x3'])
+    ap.add_argument('--precision', default=os.environ.get('OG_PRECISION', 'fp16x3'), choices=['fp32', 'tf32x3', 'fp16x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-verify', action='store_true', help='skip the check of the timed output against tests/golden/<workload>_planted.pt')
     ap.add_argument('--cuda-graph', type=int, default=1, help='replay the launch schedule from a CUDA graph (default on)')
@@ -420,7 +420,7 @@ def main():
     p = lambda t, off=0: C.c_void_p(t.data_ptr() + off * 4)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    if args.precision == 'tf32x3':
+    if args.precision == 'tf32x3' or (args.precision == 'fp16x3' and d // H != 64):    # head_dim 32 runs the tf32 form in either mode
         kk = torch.randn(nb * n, d, device=dev)
         ldv = (n + 3) // 4 * 4
         vt = torch.randn(nb * d, ldv, device=dev)
@@ -432,7 +432,7 @@ def main():
         def attn():
             _cabi.check(lib.og_attention_tc_fwd(p(qq), d, n * d, p(khi), p(klo), d, p(vthi), p(vtlo), ldv, p(o), d, n * d,
                                                 nb, n, n, H, d // H, st), 'og_attention_tc_fwd')
-    elif args.precision == 'fp16x3':
+    elif args.precision == 'fp16x3' and d // H == 64:
         def split16(x2d):
             hi = torch.empty(x2d.shape, dtype=torch.float16, device=dev)
             lo, meta = torch.empty_like(hi), torch.zeros(4, device=dev)
@@ -509,7 +509,7 @@ def main():
                      'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops,
                      # the kernel runs 3 MMAs per algorithmic product (fp32-grade accuracy is part of the contract): its own ceiling
                      # is bf16_peak / 6 with tf32 operands (half rate) and bf16_peak / 3 with fp16 operands
-                     'frac_of_3x_ceiling': (attn_tflops / (peaks['bf16_tflops'] / {'tf32x3': 6.0, 'fp16x3': 3.0}[args.precision])
+                     'frac_of_3x_ceiling': (attn_tflops / (peaks['bf16_tflops'] / (3.0 if (args.precision == 'fp16x3' and d // H == 64) else 6.0))
                                             if args.precision != 'fp32' else None)},
         'roofline_sinkhorn': {'kernel': 'sinkhorn (%d pairs, %d iterations, one launch)' % (batch, iters), 'bound': 'hbm',
                               'achieved': sink_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',

@@ -1,4 +1,5 @@
-// fp16 hi/lo fused attention, "ping-pong" form: the production kernel of OG_PREC_FP16X3.
+// fp16 hi/lo fused attention, "ping-pong" form (measured alternative: the exponential phase of a whole 64-column row per thread is
+// MUFU-paced at ~1150 cycles; the two-teams form of csrc/attention_f16t.cuh is faster and is the default).
 //
 // Same arithmetic, operands and TMEM layout as csrc/attention_f16.cuh; what changes is who does the softmax.  With fp16
 // operands a key block costs the tensor pipe 768 cycles (24 MMAs), but the column-split softmax needs ~1650 cycles per block:
@@ -483,10 +484,12 @@ inline int attention_f16p_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   return OG_OK;
 }
 
-// OG_ATTN_FORM selects the softmax organisation of the fp16 attention: 2 (default) = ping-pong warpgroups (this file), 1 = two teams of
-// two warpgroups (csrc/attention_f16t.cuh, slower: spills), 0 = one team, column split (csrc/attention_f16.cuh).  All parity-tested.
+// OG_ATTN_FORM selects the softmax organisation of the fp16 attention (all parity-tested; self layer of the headline config):
+//   1 (default) two teams of two warpgroups on alternate key blocks (csrc/attention_f16t.cuh)   0.360 ms  381 TF/s
+//   0           one team of two warpgroups, column split (csrc/attention_f16.cuh)               0.417 ms  329 TF/s
+//   2           ping-pong: two warpgroups, a whole 64-column row per thread (this file)         0.428 ms  322 TF/s
 inline int& attention_f16_form() {
-  static int v = [] { const char* e = getenv("OG_ATTN_FORM"); return e ? atoi(e) : 2; }();
+  static int v = [] { const char* e = getenv("OG_ATTN_FORM"); return e ? atoi(e) : 1; }();
   return v;
 }
 

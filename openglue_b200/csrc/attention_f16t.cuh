@@ -11,7 +11,9 @@
 // Within a team the two warpgroups split a block by columns exactly as before (half-row maxima through shared memory and
 // one 256-thread named barrier).  The element-wise chain uses the packed fp32x2 instructions (FFMA2 / FADD2): one issue
 // slot for two logits.  20 warps: 0-7 team 0, 8-15 team 1, 16 TMA, 17 QK^T issue + TMEM, 18 P.V issue; setmaxnreg moves the
-// producer warps' registers to the softmax warpgroups.
+// producer warps' registers to the softmax warpgroups (104 registers: no spills; with the accumulators spilled the kernel ran at half
+// the speed - 256 KB of local-memory traffic per key block through the same 128 B/clk port as shared memory).
+// Measured (self layer, 32 x 4 x 2048 x 2048): 0.360 ms = 381 TF/s against 0.417 ms for the one-team form.
 #pragma once
 #include "tc_common.cuh"
 #include "attention_f16.cuh"     // F16AttnScales, TcAttnArgs

@@ -54,9 +54,10 @@ def _gnn_params(num_stages: int, d: int) -> nn.Module:
 class SuperGlue(nn.Module):
     """B200-native matching core behind the reference's module API.
 
-    Extra (optional) config keys, ignored by the reference: ``precision`` ('tf32x3' (default): tcgen05 tensor
-    cores with error-compensated tf32 | 'fp16x3': the same three-product scheme on fp16 hi/lo operands with
-    power-of-two tensor scales, twice the MMA rate | 'fp32': CUDA-core FFMA everywhere),
+    Extra (optional) config keys, ignored by the reference: ``precision`` ('fp16x3' (default): tcgen05 tensor cores,
+    every contraction as three products of fp16 hi/lo operands with power-of-two tensor scales (head_dim 64; other
+    shapes run as 'tf32x3') | 'tf32x3': the same scheme on tf32 hi/lo operands, half the MMA rate | 'fp32': CUDA-core
+    FFMA everywhere),
     ``match_threshold`` (used by :class:`MatchingCore`).
     """
 
@@ -99,7 +100,7 @@ class SuperGlue(nn.Module):
     # ------------------------------------------------------------------ weights
     def _precision(self) -> int:
         return {'fp32': _cabi.OG_PREC_FP32, 'tf32x3': _cabi.OG_PREC_TF32X3,
-                'fp16x3': _cabi.OG_PREC_FP16X3}[self.config.get('precision', 'tf32x3')]
+                'fp16x3': _cabi.OG_PREC_FP16X3}[self.config.get('precision', 'fp16x3')]
 
     def og_config(self) -> _cabi.OgConfig:
         return _cabi.make_config(self.config, self.config.get('match_threshold', 0.2), self._precision())

@@ -73,6 +73,61 @@ if which in ('qkv', 'evidence'):
             outs = (None, None, None, None) if kind == 'q' else (p(Yhi), p(Ylo), None, None)
         for _ in range(reps):
             _cabi.check(lib.og_linear_tc_fwd(C.byref(a), p(Whi), p(Wlo), *outs, 2, st), 'qkv ' + kind)
+if which in ('f16', 'evidence16'):
+    # the fp16 hi/lo kernels at the headline shapes: self attention, cross attention, Q / K / V projections, fc1, fc2
+    def split16(x2d, bias=None):
+        hi = torch.empty(x2d.shape, dtype=torch.float16, device=dev)
+        lo, meta = torch.empty_like(hi), torch.zeros(4, device=dev)
+        _cabi.check(lib.og_weight_split_f16(p(x2d), p(bias), x2d.shape[0], x2d.shape[1], p(hi), p(lo), p(meta), st), 'split16')
+        return hi, lo, meta
+
+    def amax(x):
+        s_ = torch.zeros(1, device=dev)
+        _cabi.check(lib.og_amax(p(x), x.numel(), p(s_), st), 'amax')
+        return s_
+    for nb in (2 * B, B):                                   # self layer (32 sequences), cross layer (16)
+        q = torch.randn(nb * n, d, device=dev); k = torch.randn(nb * n, d, device=dev); vt = torch.randn(nb * d, n, device=dev)
+        kh, kl, km = split16(k); vh, vl, vm = split16(vt)
+        o = torch.empty(nb * n, d, device=dev)
+        qa = amax(q)
+        for _ in range(reps):
+            _cabi.check(lib.og_attention_f16_fwd(p(q), d, n * d, p(qa), p(kh), p(kl), d, p(km), p(vh), p(vl), n, p(vm), p(o), d, n * d, None,
+                                                 nb, n, n, H, d // H, 0, st), 'attention_f16')
+    rows = 2 * B * n
+    for (kind, k1, k2, nout, relu, resid) in (('q', 256, 0, 256, 0, 0), ('k', 256, 0, 256, 0, 0), ('v', 256, 0, 256, 0, 0),
+                                              ('fc1', 256, 256, 512, 1, 0), ('fc2', 512, 0, 256, 0, 1)):
+        A = torch.randn(rows, k1, device=dev)
+        A2 = torch.randn(rows, k2, device=dev) if k2 else None
+        W = torch.randn(nout, k1 + k2, device=dev) / 16
+        bias = torch.randn(nout, device=dev)
+        Wh, Wl, meta = split16(W, bias)
+        am = amax(torch.cat([A.flatten(), A2.flatten()]) if k2 else A)
+        Y = torch.randn(rows, nout, device=dev)
+        a = _cabi.OgLinearArgs()
+        a.k1, a.k2, a.ldw, a.strideW = k1, k2, k1 + k2, 0
+        a.bias = bias.data_ptr()
+        a.nout, a.alpha, a.relu = nout, 1.0, relu
+        a.A, a.lda = A.data_ptr(), k1
+        if k2:
+            a.A2, a.lda2 = A2.data_ptr(), k2
+        ao, so = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        outs = [None, None, None, None]
+        if kind == 'v':
+            a.strideA, a.rows, a.batch, a.ldyt, a.strideYt = n * k1, n, 2 * B, n, nout * n
+            yt_h = torch.empty(2 * B, nout, n, dtype=torch.float16, device=dev); yt_l = torch.empty_like(yt_h)
+            outs[2], outs[3] = p(yt_h), p(yt_l)
+        else:
+            a.rows, a.batch, a.ldy = rows, 1, nout
+            if kind == 'k':
+                yh = torch.empty(rows, nout, dtype=torch.float16, device=dev); yl = torch.empty_like(yh)
+                outs[0], outs[1] = p(yh), p(yl)
+            else:
+                a.Y = Y.data_ptr()
+                if resid:
+                    a.R, a.ldr = Y.data_ptr(), nout
+        for _ in range(reps):
+            _cabi.check(lib.og_linear_f16_fwd(C.byref(a), p(Wh), p(Wl), p(meta), p(am), p(ao) if a.Y else None,
+                                              None if a.Y else p(so), *outs, 0, st), 'linear_f16 ' + kind)
 if which in ('linear', 'all'):
     rows = 2 * B * n
     for (k1, k2, nout, relu, resid) in ((256, 0, 256, 0, 0), (256, 256, 512, 1, 0), (512, 0, 256, 0, 1)):
