@@ -290,6 +290,21 @@ int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, 
                       int64_t* gt_matches0, int64_t* gt_matches1, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Batch collation of cached local features: the step that FEEDS the path from the cached-feature dataset.  Replaces
+ * MegaDepthPairsDataModuleFeatures.stack_keypoints_batch (data/megadepth_datamodule.py:105-168): per image, the
+ * `target_keypoints` most confident keypoints in descending score order (select == NULL; torch.topk, ties -> lower
+ * index) or the caller's selection (select [2*batch, target_keypoints] int32: torch.randperm indices, training), all of
+ * them + zero padding when an image has fewer; depth{0,1} [batch, H, W] images are sampled at (int(y), int(x)) of every
+ * kept keypoint (NULL: no depth).  Raw inputs are the images' features concatenated in the order (pair 0, image 0),
+ * (pair 0, image 1), (pair 1, image 0) ...: lafs [total,2,3], scores [total], desc [total,D], offsets [2*batch+1] int32;
+ * max_count = the largest image (<= 16384).  Outputs [batch, target, ...] per image side.  Index work: bit-exact.      */
+int og_collate_fwd(const float* lafs, const float* scores, const float* desc, const int* offsets, const int* select, int max_count,
+                   const float* depth0, int depth0_h, int depth0_w, const float* depth1, int depth1_h, int depth1_w,
+                   int batch, int target_keypoints, int descriptor_dim,
+                   float* out_lafs0, float* out_lafs1, float* out_scores0, float* out_scores1, float* out_desc0, float* out_desc1,
+                   float* out_depth0, float* out_depth1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Matching loss: the step immediately AFTER the matching core in the reference's training step
  * (models/matching_module.py:101).  Replaces criterion (utils/losses.py:7-53) for margin = None (every
  * shipped config): loss[0] = 'loss' (negative log-likelihood of the ground-truth assignment, mean per set and

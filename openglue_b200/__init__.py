@@ -5,11 +5,15 @@ Public surface mirrors the reference for this one path:
     MatchingCore(superglue)(data)    -> {'matches0', 'matching_scores0', 'matches1', 'matching_scores1'}
 and, for the step right before it in the reference's training / validation step:
     generate_gt_matches(data, features0, features1, positive_threshold, negative_threshold) -> (data, y_true)
-and the step right after it:
+and the steps either side of those:
+    collate_features(batch, target_num_keypoints, random)     (the cached-feature DataLoader's collate_fn, on the GPU)
     criterion(y_true, y_pred, margin=None) -> {'loss', 'metric_loss'}
+    matching_log_probs(S, dustbin_score, num_iters, reg)      (differentiable Sinkhorn: forward + backward kernels)
 """
 from .gt_matches import generate_gt_matches  # noqa: F401
+from .feature_cache import FeatureStore, collate_features  # noqa: F401
 from .losses import criterion  # noqa: F401
+from .sinkhorn import matching_log_probs  # noqa: F401
 from .superglue import MatchingCore, PendingMatches, SuperGlue  # noqa: F401
 
 __version__ = '0.1.0'

@@ -85,6 +85,7 @@ SYMBOLS = {
     'og_match_workspace_bytes': (_L, [_I, _I, _I]),
     'og_match_fwd': (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _L, _P]),
     'og_gt_matches_workspace_bytes': (_L, [_I, _I, _I]),
+    'og_collate_fwd': (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'og_criterion_workspace_bytes': (_L, [_I]),
     'og_criterion_fwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _F, _P, _L, _P]),
     'og_gt_matches_fwd': (_I, [_P, _P, _I, _I, _I, C.POINTER(OgGtTransform), _P, _P, _P, _L, _P]),

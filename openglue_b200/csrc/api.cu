@@ -15,6 +15,7 @@
 #include "match.cuh"
 #include "gt_matches.cuh"
 #include "criterion.cuh"
+#include "collate.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -360,6 +361,25 @@ int og_gt_matches_fwd(const float* kpts0, const float* kpts1, int batch, int n, 
                  "gt_matches: depth image sizes");
   }
   return gt_matches_launch(kpts0, kpts1, batch, n, m, *tf, gt_matches0, gt_matches1, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int og_collate_fwd(const float* lafs, const float* scores, const float* desc, const int* offsets, const int* select, int max_count,
+                   const float* depth0, int depth0_h, int depth0_w, const float* depth1, int depth1_h, int depth1_w,
+                   int batch, int target_keypoints, int descriptor_dim,
+                   float* out_lafs0, float* out_lafs1, float* out_scores0, float* out_scores1, float* out_desc0, float* out_desc1,
+                   float* out_depth0, float* out_depth1, void* stream) {
+  OG_CHECK_ARG(lafs && scores && desc && offsets && out_lafs0 && out_lafs1 && out_scores0 && out_scores1 && out_desc0 && out_desc1,
+               "collate: null pointer");
+  OG_CHECK_ARG(batch > 0 && target_keypoints > 0 && descriptor_dim > 0 && max_count >= 0, "collate: bad sizes");
+  OG_CHECK_ARG((depth0 == nullptr) == (out_depth0 == nullptr) && (depth1 == nullptr) == (out_depth1 == nullptr), "collate: depth in / out come together");
+  OG_CHECK_ARG(!depth0 || (depth0_h > 0 && depth0_w > 0), "collate: depth0 size");
+  OG_CHECK_ARG(!depth1 || (depth1_h > 0 && depth1_w > 0), "collate: depth1 size");
+  CollateArgs a;
+  a.lafs = lafs; a.scores = scores; a.desc = desc; a.offsets = offsets; a.select = select; a.depth0 = depth0; a.depth1 = depth1;
+  a.B = batch; a.K = target_keypoints; a.D = descriptor_dim; a.h0 = depth0_h; a.w0 = depth0_w; a.h1 = depth1_h; a.w1 = depth1_w;
+  a.out_lafs0 = out_lafs0; a.out_lafs1 = out_lafs1; a.out_scores0 = out_scores0; a.out_scores1 = out_scores1;
+  a.out_desc0 = out_desc0; a.out_desc1 = out_desc1; a.out_depth0 = out_depth0; a.out_depth1 = out_depth1; a.sort_n = 1;
+  return collate_launch(a, std::max(max_count, 1), (cudaStream_t)stream);
 }
 
 int64_t og_criterion_workspace_bytes(int batch) { return batch > 0 ? criterion_workspace_bytes(batch) : -1; }

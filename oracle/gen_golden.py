@@ -53,6 +53,7 @@ class _StubFinder:
         m.__loader__ = self
         if spec.name == 'pytorch_lightning':
             m.LightningModule = torch.nn.Module
+            m.LightningDataModule = type('LightningDataModule', (), {})
         if spec.name == 'torchmetrics':
             m.Metric = type('Metric', (torch.nn.Module,), {})
         if spec.name == 'kornia.feature.laf':
