@@ -13,8 +13,8 @@
 // Data movement per 64-wide K block: the raw fp32 A tile (two 128 x 32 TMA boxes, 32 KB) and the B_hi / B_lo fp16 tiles
 // ([128 or 64 rows] x 64 halves = 128-byte swizzled rows).  Four converter warps read their A row from smem, scale, split
 // and pack it (element 2c in the low half of 32-bit column c) and tcgen05.st it into a TMEM ring: A is a TMEM operand.
-// 16 warps: WG0 / WG1 = accumulate + epilogue (output columns [0,64) / [64,128)), WG2 = converters, warp 12 = TMA producer,
-// warp 13 = MMA issue + TMEM alloc.  PAIR = cta_group::2 (256 rows x 128 columns per CTA pair, each CTA stages half of B).
+// 16 warps: WG0 / WG1 = accumulate + epilogue (output columns [0,64) / [64,128)), WG2 = converters, warps 12 / 14 = TMA producers
+// of the A / B rings, warp 13 = MMA issue + TMEM alloc.  PAIR = cta_group::2 (256 rows x 128 columns per CTA pair, each CTA stages half of B).
 //
 // OUTK: 1 = fp32 Y through TMA (bias / ReLU, residual through TMA with RTMA, amax tracking)
 //       2 = row-major fp16 hi / lo through TMA (K operand of the attention kernel)
@@ -56,24 +56,30 @@ constexpr int TMEM_COLS = 512;            // acc buffers [0,128) [128,256); A ri
 constexpr int COL_A = 256;
 constexpr int OUT_TILE = 128 * 128;       // one staging tile: [128 rows x 32 fp32] or [128 rows x 64 fp16] (128-byte rows)
 constexpr int OUT_BYTES = 2 * 2 * OUT_TILE;
-constexpr int MAX_STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int CHUNK_KB = 2;               // K blocks per accumulator chunk: K = 128 = 8 k-steps x 3 MMAs = 24 accumulations into TMEM,
                                           // the same count (and therefore the same truncation error) as the tf32 form's K = 64 chunks
 
+// Two rings: the fp32 A tile's slot is free again as soon as the converters have read it (~1000 cycles after it landed), the B
+// tiles' slot only when the MMAs that read it have retired (~2000 cycles later).  With ONE ring of three 48 KB stages a stage
+// lived ~3300 cycles (load 1400 + convert 1000 + MMA 900: event trace profiles/r02_trace_gemm_f16_fc2_v1.txt) = one K block per
+// 1100 cycles against 768 of MMA work; the 16 KB B stages are cheap to deepen.
 template <int PAIR> struct Cfg {
-  static constexpr int STAGES = PAIR ? 3 : 2;
+  static constexpr int A_STAGES = 3;                          // = depth of the TMEM A ring
+  static constexpr int B_STAGES = PAIR ? 4 : 2;
   static constexpr int BROWS = BN / (PAIR ? 2 : 1);
   static constexpr int B_TILE = BROWS * 128;                  // bytes of its B_hi (or B_lo) part: BROWS rows x 64 halves
-  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_TILE;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + 2048;
+  static constexpr int B_STAGE = 2 * B_TILE;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_BYTES + B_STAGES * B_STAGE + OUT_BYTES + 1536;   // 231936 of 232448 bytes
 };
 
 struct __align__(16) Barriers {
-  uint64_t a_land[MAX_STAGES], b_full[MAX_STAGES], empty[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
+  uint64_t a_land[MAX_STAGES], a_free[MAX_STAGES], b_full[MAX_STAGES], b_free[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
   uint64_t acc_full[2], acc_empty[2], r_full[2];
   uint32_t tmem_base;
   alignas(16) float bias[2][BN];
 };
+static_assert(sizeof(Barriers) <= 1536, "Barriers must fit the tail of the shared-memory budget");
 struct Sched { int ntmg, ntn, ngroups, nkb, nchunks; };
 }  // namespace tcf
 
@@ -90,12 +96,14 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
   using namespace tcf;
   using namespace tc;
   using C = Cfg<PAIR>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE = C::B_TILE, NC = PAIR ? 2 : 1;
+  constexpr int AST = C::A_STAGES, BST = C::B_STAGES, B_TILE = C::B_TILE, B_STAGE = C::B_STAGE, NC = PAIR ? 2 : 1;
   constexpr bool r_tma = RTMA != 0;
   launch_dependents();
   extern __shared__ uint8_t og_tcf_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcf_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_out = smem + STAGES * STAGE_BYTES;                          // [2 warpgroups][2 buffers][16 KB]
+  uint8_t* sm_a = smem;                                                  // [AST][32 KB] raw fp32 A tiles
+  uint8_t* sm_b = smem + AST * A_BYTES;                                  // [BST][B_hi | B_lo]
+  uint8_t* s_out = sm_b + BST * B_STAGE;                                  // [2 warpgroups][2 buffers][16 KB]
   Barriers* bars = reinterpret_cast<Barriers*>(s_out + OUT_BYTES);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -103,11 +111,11 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
   const int g_first = blockIdx.x / NC, g_stride = gridDim.x / NC;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&bars->a_land[i], 1); mbar_init(&bars->b_full[i], 1);
-      mbar_init(&bars->empty[i], 4 + 1);                     // 4 converter warps + the MMA commit
+    for (int i = 0; i < AST; ++i) {
+      mbar_init(&bars->a_land[i], 1); mbar_init(&bars->a_free[i], 4);      // 4 converter warps have read the smem tile
       mbar_init(&bars->a_full[i], 4 * NC); mbar_init(&bars->a_empty[i], 1);
     }
+    for (int i = 0; i < BST; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_free[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 8 * NC); mbar_init(&bars->r_full[i], 1); }
     fence_barrier_init();
     prefetch_tensormap(&map_a); prefetch_tensormap(&map_a2);
@@ -147,18 +155,17 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
 
   if (warp >= 12) {
   if (warp == 12) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer of the fp32 A tiles
     if (elect_one()) {
       int it = 0;
       for (int t = g_first; t < sc.ngroups; t += g_stride) {
         int m0, n0, bz; tile_coords(t, m0, n0, bz);
         const int arow = bz * a.rows + m0;
-        const int brow = n0 + bz * a.b_rows_per_batch + (int)crank * C::BROWS;
         for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&bars->empty[s], ph ^ 1);
+          const int s = it % AST, ph = (it / AST) & 1;
+          mbar_wait(&bars->a_free[s], ph ^ 1);
           OG_TRACE_EVT(0, it);
-          uint8_t* dst = smem + s * STAGE_BYTES;
+          uint8_t* dst = sm_a + s * A_BYTES;
           const int k = kb * BK;
           mbar_arrive_expect_tx(&bars->a_land[s], A_BYTES);    // columns beyond K arrive as zeros (TMA out-of-bounds fill)
 #pragma unroll
@@ -167,13 +174,28 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
             if (kj < a.k1 || !a.A2) tma_load_2d(dst + j * A_SUB, &map_a, &bars->a_land[s], kj, arow);      // kj >= K: all zeros
             else                    tma_load_2d(dst + j * A_SUB, &map_a2, &bars->a_land[s], kj - a.k1, arow);
           }
-          if (crank == 0) mbar_arrive_expect_tx(&bars->b_full[s], NC * 2 * B_TILE);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ TMA producer of the fp16 B tiles (own, deeper ring)
+    if (elect_one()) {
+      int it = 0;
+      for (int t = g_first; t < sc.ngroups; t += g_stride) {
+        int m0, n0, bz; tile_coords(t, m0, n0, bz);
+        const int brow = n0 + bz * a.b_rows_per_batch + (int)crank * C::BROWS;
+        for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
+          const int s = it % BST, ph = (it / BST) & 1;
+          mbar_wait(&bars->b_free[s], ph ^ 1);
+          uint8_t* dst = sm_b + s * B_STAGE;
+          const int k = kb * BK;
+          if (crank == 0) mbar_arrive_expect_tx(&bars->b_full[s], NC * B_STAGE);
           if (PAIR) {
-            tma_load_2d_pair(dst + A_BYTES, &map_bhi, &bars->b_full[s], k, brow);
-            tma_load_2d_pair(dst + A_BYTES + B_TILE, &map_blo, &bars->b_full[s], k, brow);
+            tma_load_2d_pair(dst, &map_bhi, &bars->b_full[s], k, brow);
+            tma_load_2d_pair(dst + B_TILE, &map_blo, &bars->b_full[s], k, brow);
           } else {
-            tma_load_2d(dst + A_BYTES, &map_bhi, &bars->b_full[s], k, brow);
-            tma_load_2d(dst + A_BYTES + B_TILE, &map_blo, &bars->b_full[s], k, brow);
+            tma_load_2d(dst, &map_bhi, &bars->b_full[s], k, brow);
+            tma_load_2d(dst + B_TILE, &map_blo, &bars->b_full[s], k, brow);
           }
         }
       }
@@ -189,14 +211,15 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         tc_fence_after();
         const int kb_end = min((c + 1) * CHUNK_KB, sc.nkb);
         for (int kb = c * CHUNK_KB; kb < kb_end; ++kb, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&bars->b_full[s], ph);
+          const int s = it % AST, ph = (it / AST) & 1;           // A: TMEM ring slot
+          const int sb = it % BST, phb = (it / BST) & 1;         // B: smem ring slot
+          mbar_wait(&bars->b_full[sb], phb);
           OG_TRACE_EVT(3, it);
           mbar_wait(&bars->a_full[s], ph);
           tc_fence_after();
           OG_TRACE_EVT(4, it);
           if (elect_one()) {
-            const uint32_t bhi = smem_u32(smem + s * STAGE_BYTES + A_BYTES), blo = bhi + B_TILE;
+            const uint32_t bhi = smem_u32(sm_b + sb * B_STAGE), blo = bhi + B_TILE;
             const uint32_t d = tmem + buf * 128;
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
@@ -213,7 +236,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
                 umma_f16_ts(d, ahi, dbhi, idesc, 1u);
               }
             }
-            commit(&bars->empty[s]);
+            commit(&bars->b_free[sb]);
             commit(&bars->a_empty[s]);
             if (kb == kb_end - 1) commit(&bars->acc_full[buf]);
           }
@@ -230,13 +253,13 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
     int it = 0;
     for (int t = g_first; t < sc.ngroups; t += g_stride) {
       for (int kb = 0; kb < sc.nkb; ++kb, ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int s = it % AST, ph = (it / AST) & 1;
         mbar_wait(&bars->a_land[s], ph);
         if (warp == 8 && lane == 0) OG_TRACE_EVT(1, it);
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint8_t* arow = smem + s * STAGE_BYTES + j * A_SUB + trow * 128;
+          const uint8_t* arow = sm_a + s * A_BYTES + j * A_SUB + trow * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (trow & 7)) * 16));   // undo the 128B swizzle
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
           for (int w = 0; w < 32; ++w) { hi[w] = __byte_perm(hi[w], 0, 0x1032); lo[w] = __byte_perm(lo[w], 0, 0x1032); }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->empty[s]);           // this warp is done with the smem A tile
+        if (lane == 0) mbar_arrive(&bars->a_free[s]);          // this warp is done with the smem A tile: the producer may refill it
         mbar_wait(&bars->a_empty[s], ph ^ 1);
         tc_fence_after();
         const uint32_t taddr = tmem + lane_base + COL_A + s * 64;
