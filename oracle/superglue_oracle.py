@@ -4,8 +4,8 @@ This file restates, as plain functions over a ``state_dict``, the algorithm of t
 reference's hot path (ucuapps/OpenGlue @ de2a26a).  It is the checker that the CUDA
 path in ``openglue_b200/`` is compared against.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
-legs may import it; the product package never does (tests/test_boundary.py greps
-for that).
+legs may import it; the product package never does
+(tests/test_host_logic.py::test_product_never_imports_the_oracle greps for that).
 
 Parity pin: the reference ships NO golden vectors or tests, so
 the oracle is pinned against outputs of the reference itself, produced in the

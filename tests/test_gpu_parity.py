@@ -175,6 +175,9 @@ def test_forward_matches_reference_big(golden, name, precision, pair):
     (1, 4096, 1024, dict(descriptor_dim=128, num_stages=1, num_iters=50, side_info_size=6), 'planted'),   # configs[4] shape
     (2, 330, 197, dict(descriptor_dim=256, num_stages=2, num_iters=30), 'planted'),    # head_dim 64 (the fp16x3 GNN path), ragged n != m
     (1, 200, 200, dict(descriptor_dim=256, num_stages=3, num_iters=20, use_offset=True), 'flat'),        # head_dim 64, n == m (joint self layers)
+    (1, 1, 5, dict(descriptor_dim=256, num_stages=1, num_iters=5), 'flat'),            # head_dim 64: a single keypoint / single key block tail
+    (3, 64, 1, dict(descriptor_dim=256, num_stages=2, num_iters=0), 'flat'),           # head_dim 64: one key, zero Sinkhorn iterations
+    (2, 129, 257, dict(descriptor_dim=128, num_heads=2, num_stages=2, num_iters=10, residual=False), 'planted'),   # head_dim 64 with d = 128
 ])
 @pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'fp16x3'])
 def test_forward_matches_oracle(batch, n, m, kw, family, precision):
