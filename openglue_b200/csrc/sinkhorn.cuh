@@ -39,6 +39,7 @@ struct SinkArgs {
   int SP, rows_per_strip, mpad;
   float* hist_u;                         // optional [B][iters][n+1]: u_t of every iteration  (kept for the backward pass,
   float* hist_v;                         // optional [B][iters+1][m+1]: v_t, row 0 = v_0 = 0   csrc/sinkhorn_bwd.cuh)
+  int res_q16;                           // fraction (Q16) of the rows that are loaded with the L2 evict_last policy (see sink_policy)
 };
 
 constexpr int SINK_WARPS = 8;
@@ -65,6 +66,25 @@ __device__ __forceinline__ uint32_t sink_smem_u32(const void* p) { return static
 __device__ __forceinline__ void sink_mbar_init(uint64_t* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sink_smem_u32(bar)) : "memory");
 }
+// L2 residency: the score matrix is read `iters` + 1 times and never written, but at the headline shape (16 pairs x 2048^2 x 4 B
+// = 268 MB) it is twice the L2, and with plain LRU-like replacement a cyclic sweep over it hits nothing (ncu round 1: DRAM bytes
+// = 1.01 x the algorithmic bytes).  So a FIXED subset - the first res_rows rows of every strip, ~RES_MB in total - is loaded with
+// the evict_last policy and everything else with evict_first: the subset stays in L2 across the iterations and only the rest
+// streams from HBM.  The subset is INTERLEAVED with the streamed rows (round k of a strip is kept iff floor((k+1) f) != floor(k f)):
+// with a contiguous block of resident rows every CTA would sit in its L2 phase at the same time and leave HBM idle, then all
+// stream together (measured: DRAM bytes - 22 %, time unchanged).  The final pass reads every row with evict_first, which hands
+// the lines back to the kernels that follow.
+__device__ __forceinline__ uint64_t sink_policy(bool keep) {
+  uint64_t p;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void sink_row_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sink_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(sink_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sink_smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void sink_row_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sink_smem_u32(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -76,6 +96,18 @@ __device__ __forceinline__ void sink_mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(sink_smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
+}
+
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two independent round-to-nearest operations per instruction, bit-identical to
+// the scalar forms; the sweep is issue-bound without them (ncu round 2: 53 % issue-active at 15.5 instructions per element)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float x, float y) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
 
 // V: float4s per lane of a warp's column segment (C = 128 V columns);  W: warps that share one row (a row group covers
@@ -108,6 +140,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
   const float a_reg = expf(a.norm), a_last = expf(a.log_a_last);
   const int seg_cols = min(m, c0 + C) - c0;            // <= 0: this warp's segment lies beyond the last column
   const bool has_seg = seg_cols > 0;
+  const bool seg_full = seg_cols == C;                 // warp-uniform
   const uint32_t seg_bytes = has_seg ? (uint32_t)(((seg_cols + 3) / 4) * 16) : 0u;     // <= 4 * (lds - c0): inside the padded row
   float* my_ring = ring + warp * SLOTS * C;
   uint64_t* my_bars = bars + warp * SLOTS;
@@ -121,99 +154,110 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
   __syncthreads();
 
   uint32_t issued = 0, consumed = 0;                   // per-warp ring counters (real rows only)
+  const uint64_t pol_keep = sink_policy(true), pol_stream = sink_policy(false);
+  auto keep_row = [&](int row) {                       // does this row belong to the L2-resident subset?
+    const uint32_t k = (uint32_t)(row - r0) / (uint32_t)G;
+    return ((k + 1) * (uint32_t)a.res_q16 >> 16) != (k * (uint32_t)a.res_q16 >> 16);
+  };
+  bool last_sweep = (a.iters == 0);                    // the sweep being FETCHED is the final pass (set below)
   auto prefetch_first = [&]() {                        // first SLOTS rows of this warp's group
     if (lane == 0 && has_seg) {
       for (int sl = 0; sl < SLOTS; ++sl) {
         const int row = r0 + grp + sl * G;
         if (row < r1_real) {
-          sink_row_copy(my_ring + (issued % SLOTS) * C, Sb + (int64_t)row * a.lds + c0, seg_bytes, &my_bars[issued % SLOTS]);
+          sink_row_copy(my_ring + (issued % SLOTS) * C, Sb + (int64_t)row * a.lds + c0, seg_bytes, &my_bars[issued % SLOTS],
+                        (!last_sweep && keep_row(row)) ? pol_keep : pol_stream);
           ++issued;
         }
       }
     }
   };
-  // fetch this warp's segment of row `row` into registers; refill the slot with the row SLOTS ahead
-  auto take_row = [&](int row, float4 (&z)[V]) {
+  // fetch this warp's segment of row `row` into registers (float4 k = pairs 2k, 2k+1); refill the slot with the row SLOTS ahead
+  auto take_row = [&](int row, f32x2 (&z)[2 * V]) {
     if (row < n) {
       if (has_seg) {
         const uint32_t sl = consumed % SLOTS, ph = (consumed / SLOTS) & 1;
         sink_mbar_wait(&my_bars[sl], ph);
-        const float4* src = reinterpret_cast<const float4*>(my_ring + sl * C);
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(my_ring + sl * C);
+        if (seg_full) {                                // the whole segment lies inside the row: no masks (the common case)
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const int idx = lane + 32 * k;
-          z[k] = (c0 + 4 * idx < m) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (m & 3) {                                   // the float4 that straddles column m: its tail is row padding (any bits)
+          for (int k = 0; k < V; ++k) { const ulonglong2 q = src[lane + 32 * k]; z[2 * k] = q.x; z[2 * k + 1] = q.y; }
+        } else {
 #pragma unroll
           for (int k = 0; k < V; ++k) {
-            const int c = c0 + 4 * (lane + 32 * k);
-            if (c < m && c + 3 >= m) {
-              if (c + 1 >= m) z[k].y = 0.f;
-              if (c + 2 >= m) z[k].z = 0.f;
-              z[k].w = 0.f;
+            const int idx = lane + 32 * k;
+            const int c = c0 + 4 * idx;
+            float4 q = (c < m) ? reinterpret_cast<const float4*>(src)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < m && c + 3 >= m) {                 // the float4 that straddles column m: its tail is row padding (any bits)
+              if (c + 1 >= m) q.y = 0.f;
+              if (c + 2 >= m) q.z = 0.f;
+              q.w = 0.f;
             }
+            z[2 * k] = pk2(q.x, q.y); z[2 * k + 1] = pk2(q.z, q.w);
           }
         }
         ++consumed;
         __syncwarp();                                  // every lane has its part of the row in registers
         const int nxt = row + SLOTS * G;
         if (lane == 0 && nxt < r1_real) {
-          sink_row_copy(my_ring + sl * C, Sb + (int64_t)nxt * a.lds + c0, seg_bytes, &my_bars[sl]);
+          sink_row_copy(my_ring + sl * C, Sb + (int64_t)nxt * a.lds + c0, seg_bytes, &my_bars[sl],
+                        (!last_sweep && keep_row(nxt)) ? pol_keep : pol_stream);
           ++issued;
         }
         if (!unit_reg) {
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            z[k].x = __fdiv_rn(z[k].x, a.reg); z[k].y = __fdiv_rn(z[k].y, a.reg);
-            z[k].z = __fdiv_rn(z[k].z, a.reg); z[k].w = __fdiv_rn(z[k].w, a.reg);
+          for (int k = 0; k < 2 * V; ++k) {
+            float x, y; upk2(z[k], x, y);
+            z[k] = pk2(__fdiv_rn(x, a.reg), __fdiv_rn(y, a.reg));
           }
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < V; ++k) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);     // masked through v = -inf
+        for (int k = 0; k < 2 * V; ++k) z[k] = 0ull;   // masked through v = -inf
       }
     } else {                                           // the dustbin row is the constant dustbin score
 #pragma unroll
-      for (int k = 0; k < V; ++k) z[k] = make_float4(dz, dz, dz, dz);
+      for (int k = 0; k < 2 * V; ++k) z[k] = pk2(dz, dz);
     }
   };
 
   prefetch_first();
   uint32_t rowpar = 0;                                 // parity of the exchange buffer (alternates per row of the group)
+  const f32x2 log2e2 = pk2(LOG2E_F, LOG2E_F);
   for (int it = 0; it < a.iters; ++it) {
-    float4 cacc[V];
+    if (tid == 0) OG_TRACE_EVT(0, it);
+    f32x2 cacc[2 * V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 2 * V; ++k) cacc[k] = 0ull;
     float cacc_m = 0.f;
     const float v_m = v_s[MC];
 
     for (int row = r0 + grp; row < r1; row += G) {
-      float4 z[V];
+      f32x2 z[2 * V];
       take_row(row, z);
       // t = z + v, masked; maximum over this warp's segment (the dustbin column entry belongs to segment 0)
       const float t_m = dz + v_m;
       float mx = (sub == 0) ? t_m : -CUDART_INF_F;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const int c = c0 + 4 * (lane + 32 * k);
-        const float4 vv = *reinterpret_cast<const float4*>(v_s + c);   // columns >= m: finite z + (-inf) = -inf, e = 0
-        z[k].x += vv.x; z[k].y += vv.y; z[k].z += vv.z; z[k].w += vv.w;
-        mx = fmaxf(mx, fmaxf(fmaxf(z[k].x, z[k].y), fmaxf(z[k].z, z[k].w)));
+        const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(v_s + c0 + 4 * (lane + 32 * k));   // columns >= m: finite z + (-inf) = -inf, e = 0
+        z[2 * k] = add2(z[2 * k], vv.x); z[2 * k + 1] = add2(z[2 * k + 1], vv.y);
+        float x0, x1, x2, x3; upk2(z[2 * k], x0, x1); upk2(z[2 * k + 1], x2, x3);
+        mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
       }
       mx = warp_max(mx);
       const float mxs = (mx == -CUDART_INF_F) ? 0.f : mx;               // an all-padding segment: e = 2^-inf = 0, not NaN
-      float sum = 0.f;
+      const f32x2 mxs2 = pk2(mxs, mxs);
+      f32x2 sum2a = 0ull, sum2b = 0ull;
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        z[k].x = ex2_approx((z[k].x - mxs) * LOG2E_F);
-        z[k].y = ex2_approx((z[k].y - mxs) * LOG2E_F);
-        z[k].z = ex2_approx((z[k].z - mxs) * LOG2E_F);
-        z[k].w = ex2_approx((z[k].w - mxs) * LOG2E_F);
-        sum += (z[k].x + z[k].y) + (z[k].z + z[k].w);
+      for (int k = 0; k < 2 * V; ++k) {
+        float x, y; upk2(mul2(sub2(z[k], mxs2), log2e2), x, y);
+        z[k] = pk2(ex2_approx(x), ex2_approx(y));
+        if (k & 1) sum2b = add2(sum2b, z[k]); else sum2a = add2(sum2a, z[k]);
       }
+      float sa, sb; upk2(add2(sum2a, sum2b), sa, sb);
       const float e_m = (sub == 0) ? ex2_approx((t_m - mxs) * LOG2E_F) : 0.f;
-      float s_i = warp_sum(sum) + e_m;
+      float s_i = warp_sum(sa + sb) + e_m;
       float mxg = mx, f_w = 1.f;
       if (W > 1) {                                     // combine the segments of the row: S = sum_w S_w 2^(mx_w - mx)
         float2* x = xr + (rowpar * G + grp) * W;
@@ -234,20 +278,20 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
         if (it == a.iters - 1) a.u[(int64_t)b * (n + 1) + row] = u_i;
         if (a.hist_u) a.hist_u[((int64_t)b * a.iters + it) * (n + 1) + row] = u_i;
       }
+      const f32x2 w2 = pk2(w_i, w_i);
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        cacc[k].x = fmaf(z[k].x, w_i, cacc[k].x); cacc[k].y = fmaf(z[k].y, w_i, cacc[k].y);
-        cacc[k].z = fmaf(z[k].z, w_i, cacc[k].z); cacc[k].w = fmaf(z[k].w, w_i, cacc[k].w);
-      }
+      for (int k = 0; k < 2 * V; ++k) cacc[k] = fma2(z[k], w2, cacc[k]);
       cacc_m = fmaf(e_m, w_i, cacc_m);
     }
+    if (tid == 0) OG_TRACE_EVT(1, it);
+    last_sweep = (it == a.iters - 1);
     prefetch_first();                                 // next sweep's (or the final pass's) first rows fly during the reduction
     // warp -> CTA: a row group's warps own disjoint column segments of red[grp]
     float* myred = red + grp * a.mpad;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int c = c0 + 4 * (lane + 32 * k);
-      if (c < m) *reinterpret_cast<float4*>(myred + c) = cacc[k];       // entries >= m are zero
+      if (c < m) *reinterpret_cast<ulonglong2*>(myred + c) = make_ulonglong2(cacc[2 * k], cacc[2 * k + 1]);   // entries >= m are zero
     }
     __syncthreads();                                  // (a) all float4 column sums are in `red`
     if (sub == 0 && lane == 0) myred[m] = cacc_m;     // column m = dustbin column (may overlap a float4 tail)
@@ -261,7 +305,9 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
     }
     // only the SP CTAs of this pair exchange data: a per-pair barrier (own 128-byte line) lets the pairs drift apart,
     // so HBM keeps streaming for the other pairs while one pair sits in its reduction / barrier phase
+    if (tid == 0) OG_TRACE_EVT(2, it);
     grid_barrier(a.barrier + 32 * b, (unsigned int)(it + 1) * (unsigned int)a.SP);
+    if (tid == 0) OG_TRACE_EVT(3, it);
     // every CTA of the pair rebuilds v (fixed summation order => bitwise identical across CTAs)
     const float* pb = a.partial + ((int64_t)(it & 1) * a.B * a.SP + (int64_t)b * a.SP) * a.mpad;
     // float4 columns, all SP loads of a thread in flight together (this phase is pure L2 latency: every CTA of the pair waits on it)
@@ -281,6 +327,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
       }
     }
     __syncthreads();
+    if (tid == 0) OG_TRACE_EVT(4, it);
     if (a.hist_v && strip == 0) {                     // every CTA of the pair holds the same v: one of them records it
       float* hv = a.hist_v + ((int64_t)b * (a.iters + 1) + it + 1) * (m + 1);
       for (int j = tid; j <= m; j += blockDim.x) hv[j] = (j < m) ? v_s[j] : v_s[MC];
@@ -291,8 +338,8 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
   {
     const float v_m = v_s[MC];
     for (int row = r0 + grp; row < r1; row += G) {
-      float4 z[V];
-      take_row(row, z);
+      f32x2 zp[2 * V];
+      take_row(row, zp);
       float u_i = 0.f;
       if (a.iters > 0) {
         if (lane == 0) u_i = __ldcg(a.u + (int64_t)b * (n + 1) + row);
@@ -304,10 +351,11 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
         const int c = c0 + 4 * (lane + 32 * k);
         if (c < m) {
           const float4 vv = *reinterpret_cast<const float4*>(v_s + c);
-          if (c + 0 < m) out[c + 0] = (z[k].x + u_i) + vv.x - a.norm;
-          if (c + 1 < m) out[c + 1] = (z[k].y + u_i) + vv.y - a.norm;
-          if (c + 2 < m) out[c + 2] = (z[k].z + u_i) + vv.z - a.norm;
-          if (c + 3 < m) out[c + 3] = (z[k].w + u_i) + vv.w - a.norm;
+          float z0, z1, z2, z3; upk2(zp[2 * k], z0, z1); upk2(zp[2 * k + 1], z2, z3);
+          if (c + 0 < m) out[c + 0] = (z0 + u_i) + vv.x - a.norm;
+          if (c + 1 < m) out[c + 1] = (z1 + u_i) + vv.y - a.norm;
+          if (c + 2 < m) out[c + 2] = (z2 + u_i) + vv.z - a.norm;
+          if (c + 3 < m) out[c + 3] = (z3 + u_i) + vv.w - a.norm;
         }
       }
       if (sub == 0 && lane == 0) out[m] = (dz + u_i) + v_m - a.norm;
@@ -317,6 +365,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
 
 struct SinkPlan { int V, W, slots, occ, SP, rows_per_strip, mpad, pairs_per_launch; size_t smem; };
 constexpr int SINK_MAX_COLS = 8192;
+constexpr int SINK_L2_RESIDENT_MB = 0;   // of the 126 MB L2
 
 template <int V, int W, int SLOTS>
 inline size_t sinkhorn_smem(int mpad) {
@@ -422,6 +471,12 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
     a.SP = p.SP; a.rows_per_strip = p.rows_per_strip; a.mpad = p.mpad;
     a.hist_u = hist_u ? hist_u + (int64_t)b0 * iters * (n + 1) : nullptr;
     a.hist_v = hist_v ? hist_v + (int64_t)b0 * (iters + 1) * (m + 1) : nullptr;
+    {                                                  // L2-resident subset: ~res_mb MB of this launch's matrices (OG_SINK_L2_MB, 0 = off)
+      static const int res_mb = [] { const char* e = getenv("OG_SINK_L2_MB"); return e ? atoi(e) : SINK_L2_RESIDENT_MB; }();
+      const double total = (double)nb * n * (double)m * 4.0;
+      const double frac = total > 0 ? std::min(1.0, res_mb * 1048576.0 / total) : 0.0;
+      a.res_q16 = (int)(frac * 65536.0);
+    }
     OG_CUDA(cudaMemsetAsync(barrier, 0, (size_t)nb * 128, stream));
     if (p.V == 8 && p.slots == 4)   rc = sinkhorn_launch_v<8, 2, 4>(a, p, stream);
     else if (p.V == 16 && p.W == 1) rc = sinkhorn_launch_v<16, 1, 2>(a, p, stream);

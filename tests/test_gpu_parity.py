@@ -68,7 +68,8 @@ def check_matches(ours, ref, scores_ref, tol):
     ms_ref = ref['matching_scores0']
     decisive &= (ms_ref - 0.2).abs() > 2 * tol                # threshold not within tolerance either
     assert torch.equal(m0[decisive], r0[decisive])
-    assert (ours['matching_scores0'].cpu()[decisive] - ms_ref[decisive]).abs().max() <= tol
+    if decisive.any():                                        # (a 1-keypoint image can leave no decisive row at all)
+        assert (ours['matching_scores0'].cpu()[decisive] - ms_ref[decisive]).abs().max() <= tol
     return int((~decisive).sum())
 
 
@@ -198,7 +199,8 @@ def test_forward_matches_oracle(batch, n, m, kw, family, precision):
     dec1 = col_ok & row_ok.gather(1, i1) & ((ref['matching_scores1'] - 0.2).abs() > 2 * bound)
     dec1 &= (ref['matching_scores0'].gather(1, i1) - 0.2).abs() > 2 * bound
     assert torch.equal(res['matches1'].cpu()[dec1], ref['matches1'][dec1])
-    assert (res['matching_scores1'].cpu()[dec1] - ref['matching_scores1'][dec1]).abs().max() <= bound
+    if dec1.any():
+        assert (res['matching_scores1'].cpu()[dec1] - ref['matching_scores1'][dec1]).abs().max() <= bound
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32x3', 'fp16x3'])
