@@ -315,6 +315,50 @@ int64_t og_criterion_workspace_bytes(int batch);
 int og_criterion_fwd(const float* scores, const int64_t* gt_matches0, const int64_t* gt_matches1, int batch, int n, int m,
                      float* loss, float* dscores, float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step operators: what nn.BatchNorm1d in training mode and torch autograd do for the
+ * reference around the contractions of SuperGlue.forward in MatchingTrainingModule.training_step
+ * (models/matching_module.py:71-105).  The contractions themselves (dX = dY W, dW = dY^T X, the attention gradients
+ * dV = P^T dO, dP = dO V^T, dQ = dS K, dK = dS^T Q) run on og_linear_fwd / og_linear_tc_fwd with transposed operands.
+ * Activations are row-major [rows, channels], rows = batch x keypoints.  All reductions are deterministic.
+ *   og_transpose        transpose != 0: out[b][c, r] = in[b][r, c];  == 0: pitch-changing copy.  Padding is left untouched.
+ *   og_colsum           out[c] = sum_r x[r,c] * (y ? y[r,c] - (z ? z[r,c] : 0) : 1)           (bias / mix gradients)
+ *   og_bn_train_fwd     y = gamma (r - mean) invstd + beta, r = relu ? max(a, 0) : a, batch statistics over the rows
+ *                       (biased variance), save_mean / save_invstd [cols] kept for the backward pass, running_mean /
+ *                       running_var (optional) updated with `momentum` (unbiased variance): models/utils.py:48-58,
+ *                       torch.nn.BatchNorm1d(training=True)
+ *   og_bn_train_bwd     da (through the fused ReLU), dgamma, dbeta from dy
+ *   og_softmax_rows     in-place row softmax of the materialised attention scores (models/superglue/attention.py:12-13)
+ *   og_softmax_bwd_rows dP <- scale * P * (dP - sum_j P dP)
+ *   og_axpby            out = a x + b y (y NULL: a x)
+ *   og_mix_fwd / _bwd / _param_grad   residual mix alpha = sigmoid(mix_coefs) (superglue.py:59-62) and its gradients
+ *   og_kenc_input       [2 x / (W - 1) - 1, 2 y / (H - 1) - 1, side info]  (superglue.py:74-78, positional_encoding.py:16-18)
+ * workspace: >= og_train_workspace_floats(cols) floats.                                                           */
+int64_t og_train_workspace_floats(int cols);
+/* One GEMM of the training step, args as og_linear_fwd: the tcgen05 3xTF32 kernel when the shape is tileable (K >= 32,
+ * K % 4 == 0, 16-byte aligned rows, dense batches; W is split into split_scratch, og_linear_auto_scratch_floats(args)
+ * floats, on the fly), the exact fp32 CUDA-core kernel otherwise or when precision == OG_PREC_FP32.               */
+int64_t og_linear_auto_scratch_floats(const og_linear_args* args);
+int og_linear_auto_fwd(const og_linear_args* args, int precision, float* split_scratch, void* stream);
+int og_transpose(const float* in, int64_t ld_in, int64_t stride_in, float* out, int64_t ld_out, int64_t stride_out,
+                 int batch, int rows, int cols, int transpose, void* stream);
+int og_colsum(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z, int64_t ldz, int rows, int cols,
+              float* out, float* workspace, void* stream);
+int og_bn_train_fwd(const float* a, int64_t lda, int rows, int cols, int relu, const float* gamma, const float* beta,
+                    float eps, float momentum, float* y, int64_t ldy, float* save_mean, float* save_invstd,
+                    float* running_mean, float* running_var, float* workspace, void* stream);
+int og_bn_train_bwd(const float* dy, int64_t lddy, const float* a, int64_t lda, int rows, int cols, int relu,
+                    const float* gamma, const float* save_mean, const float* save_invstd,
+                    float* da, int64_t ldda, float* dgamma, float* dbeta, float* workspace, void* stream);
+int og_softmax_rows(float* S, int64_t ld, int64_t rows, int cols, void* stream);
+int og_softmax_bwd_rows(const float* P, float* dP, int64_t ld, int64_t rows, int cols, float scale, void* stream);
+int og_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
+int og_mix_fwd(const float* g, const float* l, const float* mix, float* out, int64_t rows, int d, void* stream);
+int og_mix_bwd(const float* dm, const float* mix, float* dg, float* dl, int64_t rows, int d, void* stream);
+int og_mix_param_grad(const float* colsum, const float* mix, float* dmix, int d, void* stream);
+int og_kenc_input(const float* kpts, const float* side, int rows, int side_info_size, float width, float height,
+                  float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

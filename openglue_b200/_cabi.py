@@ -89,6 +89,21 @@ SYMBOLS = {
     'og_criterion_workspace_bytes': (_L, [_I]),
     'og_criterion_fwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _F, _P, _L, _P]),
     'og_gt_matches_fwd': (_I, [_P, _P, _I, _I, _I, C.POINTER(OgGtTransform), _P, _P, _P, _L, _P]),
+    # training-step operators (row f1)
+    'og_train_workspace_floats': (_L, [_I]),
+    'og_linear_auto_scratch_floats': (_L, [C.POINTER(OgLinearArgs)]),
+    'og_linear_auto_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P, _P]),
+    'og_transpose': (_I, [_P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _P]),
+    'og_colsum': (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P]),
+    'og_bn_train_fwd': (_I, [_P, _L, _I, _I, _I, _P, _P, _F, _F, _P, _L, _P, _P, _P, _P, _P, _P]),
+    'og_bn_train_bwd': (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P, _P, _P]),
+    'og_softmax_rows': (_I, [_P, _L, _L, _I, _P]),
+    'og_softmax_bwd_rows': (_I, [_P, _P, _L, _L, _I, _F, _P]),
+    'og_axpby': (_I, [_P, _P, _F, _F, _P, _L, _P]),
+    'og_mix_fwd': (_I, [_P, _P, _P, _P, _L, _I, _P]),
+    'og_mix_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P]),
+    'og_mix_param_grad': (_I, [_P, _P, _P, _I, _P]),
+    'og_kenc_input': (_I, [_P, _P, _I, _I, _F, _F, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

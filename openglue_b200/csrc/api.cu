@@ -16,6 +16,7 @@
 #include "gt_matches.cuh"
 #include "criterion.cuh"
 #include "collate.cuh"
+#include "train_ops.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -262,6 +263,32 @@ int og_linear_tc_fwd(const og_linear_args* a, const float* Whi, const float* Wlo
   return linear_tc_run(*a, Whi, Wlo, so, mode, (cudaStream_t)stream);
 }
 
+// one GEMM of the training step: tcgen05 3xTF32 when the shape is tileable (W is split on the fly into split_scratch, 2 x the
+// W footprint in floats), the exact fp32 CUDA-core kernel otherwise
+int64_t og_linear_auto_scratch_floats(const og_linear_args* a) {
+  if (!a || a->nout <= 0 || a->ldw <= 0 || a->batch <= 0) return -1;
+  const int64_t wf = (a->batch > 1 && a->strideW) ? (int64_t)(a->batch - 1) * a->strideW + (int64_t)a->nout * a->ldw : (int64_t)a->nout * a->ldw;
+  return 2 * align_up(wf, 64);
+}
+int og_linear_auto_fwd(const og_linear_args* a, int precision, float* split_scratch, void* stream) {
+  OG_CHECK_ARG(a && a->A && a->W && (a->Y || a->Yt), "linear_auto: null pointer");
+  OG_CHECK_ARG(a->rows > 0 && a->nout > 0 && a->batch > 0 && a->k1 > 0 && a->k2 >= 0, "linear_auto: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision != OG_PREC_FP32 && split_scratch && (!a->strideW || a->strideW % a->ldw == 0)) {
+    const int64_t half = og_linear_auto_scratch_floats(a) / 2;
+    const int64_t wf = (a->batch > 1 && a->strideW) ? (int64_t)(a->batch - 1) * a->strideW + (int64_t)a->nout * a->ldw : (int64_t)a->nout * a->ldw;
+    float* hi = split_scratch; float* lo = split_scratch + half;
+    TcLinearArgs t = to_tc_args(*a);
+    if (linear_tc2_eligible(t, hi, lo, a->ldw) && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0) {
+      split_tf32_kernel<<<(unsigned)((wf + 255) / 256), 256, 0, st>>>(a->W, hi, lo, wf);
+      OG_LAUNCH_CHECK("split_tf32_kernel");
+      launch_counter()++;
+      return linear_tc_run(*a, hi, lo, SplitOut(), 2, st);
+    }
+  }
+  return linear_simt_launch(*a, st);
+}
+
 int og_split_tf32(const float* src, float* hi, float* lo, int64_t n, void* stream) {
   OG_CHECK_ARG(src && hi && lo && n > 0, "split_tf32: bad arguments");
   split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, hi, lo, n);
@@ -390,6 +417,125 @@ int og_criterion_fwd(const float* scores, const int64_t* gt_matches0, const int6
   OG_CHECK_ARG(batch > 0 && n > 0 && m > 0, "criterion: bad sizes");
   return criterion_launch(scores, gt_matches0, gt_matches1, batch, n, m, loss, dscores, grad_scale, workspace, workspace_bytes,
                           (cudaStream_t)stream);
+}
+
+// ---- training-step operators (row f1; csrc/train_ops.cuh) ----
+int64_t og_train_workspace_floats(int cols) { return cols > 0 ? colreduce_workspace_floats(cols) + 2 * (int64_t)cols : -1; }
+
+int og_transpose(const float* in, int64_t ld_in, int64_t stride_in, float* out, int64_t ld_out, int64_t stride_out,
+                 int batch, int rows, int cols, int transpose, void* stream) {
+  OG_CHECK_ARG(in && out, "transpose: null pointer");
+  OG_CHECK_ARG(batch >= 0 && rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= (transpose ? rows : cols), "transpose: bad sizes");
+  return transpose_launch(in, ld_in, stride_in, out, ld_out, stride_out, batch, rows, cols, transpose, (cudaStream_t)stream);
+}
+
+int og_colsum(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* z, int64_t ldz, int rows, int cols,
+              float* out, float* workspace, void* stream) {
+  OG_CHECK_ARG(x && out && workspace, "colsum: null pointer");
+  OG_CHECK_ARG(rows >= 0 && cols > 0 && (!z || y), "colsum: bad arguments");
+  ColReduceArgs a = {};
+  a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.z = z; a.ldz = ldz; a.rows = rows; a.cols = cols; a.partial = workspace; a.out0 = out;
+  return colreduce_launch<0>(a, (cudaStream_t)stream);
+}
+
+int og_bn_train_fwd(const float* a_, int64_t lda, int rows, int cols, int relu, const float* gamma, const float* beta,
+                    float eps, float momentum, float* y, int64_t ldy, float* save_mean, float* save_invstd,
+                    float* running_mean, float* running_var, float* workspace, void* stream) {
+  OG_CHECK_ARG(a_ && gamma && beta && y && save_mean && save_invstd && workspace, "bn_train_fwd: null pointer");
+  OG_CHECK_ARG(rows > 0 && cols > 0, "bn_train_fwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* var = workspace;                                   // [cols]
+  ColReduceArgs r = {};
+  r.x = a_; r.ldx = lda; r.rows = rows; r.cols = cols; r.relu = relu; r.partial = workspace + 2 * (int64_t)cols; r.out0 = save_mean;
+  int rc = colreduce_launch<1>(r, st);
+  if (rc != OG_OK) return rc;
+  r.mu = save_mean; r.out0 = var;
+  if ((rc = colreduce_launch<2>(r, st)) != OG_OK) return rc;
+  bn_finish_stats_kernel<<<cdiv(cols, 256), 256, 0, st>>>(save_mean, var, cols, rows, eps, momentum, save_invstd, running_mean, running_var);
+  OG_LAUNCH_CHECK("bn_finish_stats_kernel");
+  bn_apply_kernel<<<eltwise_grid((int64_t)rows * cols), 256, 0, st>>>(a_, lda, rows, cols, relu, save_mean, save_invstd, gamma, beta, y, ldy);
+  OG_LAUNCH_CHECK("bn_apply_kernel");
+  launch_counter() += 2;
+  return OG_OK;
+}
+
+int og_bn_train_bwd(const float* dy, int64_t lddy, const float* a_, int64_t lda, int rows, int cols, int relu,
+                    const float* gamma, const float* save_mean, const float* save_invstd,
+                    float* da, int64_t ldda, float* dgamma, float* dbeta, float* workspace, void* stream) {
+  OG_CHECK_ARG(dy && a_ && gamma && save_mean && save_invstd && da && dgamma && dbeta && workspace, "bn_train_bwd: null pointer");
+  OG_CHECK_ARG(rows > 0 && cols > 0, "bn_train_bwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  ColReduceArgs r = {};
+  r.x = dy; r.ldx = lddy; r.y = a_; r.ldy = lda; r.mu = save_mean; r.invstd = save_invstd; r.rows = rows; r.cols = cols; r.relu = relu;
+  r.partial = workspace + 2 * (int64_t)cols; r.out0 = dbeta; r.out1 = dgamma;
+  int rc = colreduce_launch<3>(r, st);
+  if (rc != OG_OK) return rc;
+  bn_bwd_apply_kernel<<<eltwise_grid((int64_t)rows * cols), 256, 0, st>>>(dy, lddy, a_, lda, rows, cols, relu, save_mean, save_invstd, gamma,
+                                                                            dgamma, dbeta, da, ldda);
+  OG_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_softmax_rows(float* S, int64_t ld, int64_t rows, int cols, void* stream) {
+  OG_CHECK_ARG(S && rows >= 0 && cols > 0 && ld >= cols, "softmax_rows: bad arguments");
+  if (rows == 0) return OG_OK;
+  OG_CHECK_ARG((rows + 7) / 8 <= 0x7fffffffLL, "softmax_rows: too many rows");
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, ld, rows, cols);
+  OG_LAUNCH_CHECK("softmax_rows_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_softmax_bwd_rows(const float* P, float* dP, int64_t ld, int64_t rows, int cols, float scale, void* stream) {
+  OG_CHECK_ARG(P && dP && rows >= 0 && cols > 0 && ld >= cols, "softmax_bwd_rows: bad arguments");
+  if (rows == 0) return OG_OK;
+  OG_CHECK_ARG((rows + 7) / 8 <= 0x7fffffffLL, "softmax_bwd_rows: too many rows");
+  softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, dP, ld, rows, cols, scale);
+  OG_LAUNCH_CHECK("softmax_bwd_rows_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_axpby(const float* x, const float* y, float a_, float b, float* out, int64_t n, void* stream) {
+  OG_CHECK_ARG(x && out && n >= 0, "axpby: bad arguments");
+  if (n == 0) return OG_OK;
+  axpby_kernel<<<eltwise_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, a_, b, out, n);
+  OG_LAUNCH_CHECK("axpby_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_mix_fwd(const float* g, const float* l, const float* mix, float* out, int64_t rows, int d, void* stream) {
+  OG_CHECK_ARG(g && l && mix && out && rows > 0 && d > 0, "mix_fwd: bad arguments");
+  mix_fwd_kernel<<<eltwise_grid(rows * d), 256, 0, (cudaStream_t)stream>>>(g, l, mix, out, rows, d);
+  OG_LAUNCH_CHECK("mix_fwd_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_mix_bwd(const float* dm, const float* mix, float* dg, float* dl, int64_t rows, int d, void* stream) {
+  OG_CHECK_ARG(dm && mix && (dg || dl) && rows > 0 && d > 0, "mix_bwd: bad arguments");
+  mix_bwd_kernel<<<eltwise_grid(rows * d), 256, 0, (cudaStream_t)stream>>>(dm, mix, dg, dl, rows, d);
+  OG_LAUNCH_CHECK("mix_bwd_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_mix_param_grad(const float* colsum, const float* mix, float* dmix, int d, void* stream) {
+  OG_CHECK_ARG(colsum && mix && dmix && d > 0, "mix_param_grad: bad arguments");
+  mix_param_grad_kernel<<<cdiv(d, 256), 256, 0, (cudaStream_t)stream>>>(colsum, mix, dmix, d);
+  OG_LAUNCH_CHECK("mix_param_grad_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+int og_kenc_input(const float* kpts, const float* side, int rows, int side_info_size, float width, float height, float* out, void* stream) {
+  OG_CHECK_ARG(kpts && out && rows > 0 && side_info_size >= 0 && (side_info_size == 0 || side), "kenc_input: bad arguments");
+  kenc_input_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(kpts, side, rows, side_info_size, width - 1.f, height - 1.f, out);
+  OG_LAUNCH_CHECK("kenc_input_kernel");
+  launch_counter()++;
+  return OG_OK;
 }
 
 static int forward_impl(const og_config* cfg, const float* Wp, const float* Whi, const float* Wlo, const __half* W16h,

@@ -234,7 +234,15 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
 
     for (int row = r0 + grp; row < r1; row += G) {
       f32x2 z[2 * V];
+#ifdef OG_TRACE
+      const int tr = (it == 20 && tid == 0) ? (row - r0) / G : 1 << 20;     // row timeline of warp 0 in iteration 20
+#define OG_SINK_ROW_EVT(e) OG_TRACE_EVT(e, tr)
+#else
+#define OG_SINK_ROW_EVT(e) do { } while (0)
+#endif
+      OG_SINK_ROW_EVT(5);
       take_row(row, z);
+      OG_SINK_ROW_EVT(6);
       // t = z + v, masked; maximum over this warp's segment (the dustbin column entry belongs to segment 0)
       const float t_m = dz + v_m;
       float mx = (sub == 0) ? t_m : -CUDART_INF_F;
@@ -246,6 +254,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
         mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
       }
       mx = warp_max(mx);
+      OG_SINK_ROW_EVT(7);
       const float mxs = (mx == -CUDART_INF_F) ? 0.f : mx;               // an all-padding segment: e = 2^-inf = 0, not NaN
       const f32x2 mxs2 = pk2(mxs, mxs);
       f32x2 sum2a = 0ull, sum2b = 0ull;
@@ -258,6 +267,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
       float sa, sb; upk2(add2(sum2a, sum2b), sa, sb);
       const float e_m = (sub == 0) ? ex2_approx((t_m - mxs) * LOG2E_F) : 0.f;
       float s_i = warp_sum(sa + sb) + e_m;
+      OG_SINK_ROW_EVT(8);
       float mxg = mx, f_w = 1.f;
       if (W > 1) {                                     // combine the segments of the row: S = sum_w S_w 2^(mx_w - mx)
         float2* x = xr + (rowpar * G + grp) * W;
@@ -272,6 +282,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
         f_w = ex2_approx((mx - mxg) * LOG2E_F);
         rowpar ^= 1u;
       }
+      OG_SINK_ROW_EVT(9);
       const float w_i = __fdiv_rn((row < n) ? a_reg : a_last, s_i) * f_w;
       if ((it == a.iters - 1 || a.hist_u) && sub == 0 && lane == 0) {
         const float u_i = ((row < n) ? a.norm : a.log_a_last) - (mxg + logf(s_i));
@@ -282,6 +293,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
 #pragma unroll
       for (int k = 0; k < 2 * V; ++k) cacc[k] = fma2(z[k], w2, cacc[k]);
       cacc_m = fmaf(e_m, w_i, cacc_m);
+      OG_SINK_ROW_EVT(10);
     }
     if (tid == 0) OG_TRACE_EVT(1, it);
     last_sweep = (it == a.iters - 1);

@@ -43,13 +43,34 @@ def _run(y_true: Dict[str, torch.Tensor], y_pred: Dict[str, torch.Tensor], want_
     return loss, dscores
 
 
+class _Criterion(torch.autograd.Function):
+    """loss = criterion(scores): the same kernel call also writes d loss / d scores, which the backward pass scales."""
+
+    @staticmethod
+    def forward(ctx, scores, gt0, gt1):
+        loss, dscores = _run({'gt_matches0': gt0, 'gt_matches1': gt1}, {'scores': scores}, True, 1.0)
+        ctx.save_for_backward(dscores)
+        ctx.dtype = scores.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        dscores, = ctx.saved_tensors
+        return (dscores * gloss[0]).to(ctx.dtype), None, None          # metric_loss (loss[1]) is identically 0
+
+
 def criterion(y_true: Dict[str, torch.Tensor], y_pred: Dict[str, torch.Tensor], margin: Optional[float] = None
               ) -> Dict[str, torch.Tensor]:
-    """reference utils/losses.py:7-53 -> {'loss', 'metric_loss'} (0-dim tensors on the scores' device)."""
+    """reference utils/losses.py:7-53 -> {'loss', 'metric_loss'} (0-dim tensors on the scores' device).  Differentiable
+    with respect to ``y_pred['scores']`` (the sparse scatter the gather's backward pass is), so
+    ``criterion(...)['loss'].backward()`` drives the training step as it does in the reference (matching_module.py:101-105)."""
     if margin is not None:
         raise NotImplementedError('openglue_b200.criterion implements margin=None (every shipped reference config); '
                                   'the triplet terms of utils/losses.py:56-99 are not built')
-    loss, _ = _run(y_true, y_pred, False, 1.0)
+    if torch.is_grad_enabled() and y_pred['scores'].requires_grad:
+        loss = _Criterion.apply(y_pred['scores'], y_true['gt_matches0'], y_true['gt_matches1'])
+    else:
+        loss, _ = _run(y_true, y_pred, False, 1.0)
     return {'loss': loss[0], 'metric_loss': loss[1]}
 
 

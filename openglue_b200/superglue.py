@@ -184,8 +184,8 @@ class SuperGlue(nn.Module):
     def run(self, data: dict, want_matches: bool, want_context: bool = True,
             match_threshold: Optional[float] = None) -> Dict[str, torch.Tensor]:
         if self.training:
-            raise RuntimeError('openglue_b200.SuperGlue implements the eval-mode forward pass only '
-                               '(train-mode BatchNorm statistics and backward are not built yet)')
+            raise RuntimeError('openglue_b200.SuperGlue.run is the fused eval-mode path; in train() mode call forward() '
+                               '(openglue_b200.training: batch-statistics BatchNorm + the explicit backward pass)')
         k0, k1 = data['keypoints0'], data['keypoints1']
         dev = k0.device
         if dev.type != 'cuda':
@@ -254,7 +254,12 @@ class SuperGlue(nn.Module):
         return out
 
     def forward(self, data: dict) -> Dict[str, torch.Tensor]:
-        """-> {'context_descriptors0' [B,d,N], 'context_descriptors1' [B,d,M], 'scores' [B,N+1,M+1]}"""
+        """-> {'context_descriptors0' [B,d,N], 'context_descriptors1' [B,d,M], 'scores' [B,N+1,M+1]}.
+        In ``train()`` mode the outputs are differentiable with respect to every parameter and the local descriptors
+        (BatchNorm uses batch statistics and updates its running buffers, as the reference module does in training_step)."""
+        if self.training:
+            from .training import train_forward
+            return train_forward(self, data)
         return self.run(data, want_matches=False)
 
 

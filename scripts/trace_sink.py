@@ -37,3 +37,19 @@ for cta in range(2):
     print('   %-24s %9.0f' % ('iteration', tot))
     for i in (20, 21, 22):
         print('   it %d:' % i, [ev(e, i) - ev(0, 20) for e in range(5)])
+
+# row timeline of warp 0 (iteration 20): events 5 loop top, 6 row in registers, 7 after warp max, 8 after warp sum, 9 after the segment exchange, 10 row done
+rn = ['wait + load row', 'add v, max (shuffles)', 'exp, sum (shuffles)', 'segment exchange (bar)', 'divide, column fma', 'loop back']
+for cta in range(2):
+    ev = lambda e, i: buf[cta * 4096 + e * 256 + i]
+    rows = [i for i in range(1, 255) if ev(10, i) > 0 and ev(5, i + 1) > 0]
+    if not rows: continue
+    acc = [0.0] * 6
+    for i in rows:
+        d = [ev(6, i) - ev(5, i), ev(7, i) - ev(6, i), ev(8, i) - ev(7, i), ev(9, i) - ev(8, i), ev(10, i) - ev(9, i), ev(5, i + 1) - ev(10, i)]
+        for k in range(6): acc[k] += d[k]
+    tot = sum(acc) / len(rows)
+    print('CTA %d warp 0, iteration 20: cycles per row over %d rows' % (cta, len(rows)))
+    for k in range(6): print('   %-26s %7.0f  (%4.1f %%)' % (rn[k], acc[k] / len(rows), 100 * acc[k] / len(rows) / tot))
+    print('   %-26s %7.0f' % ('row', tot))
+    print('   first rows:', [[ev(e, i) - ev(5, 1) for e in range(5, 11)] for i in (1, 2, 3, 4)])
