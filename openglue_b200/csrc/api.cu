@@ -157,7 +157,9 @@ static int linear_tc_run(const og_linear_args& a, const float* Whi, const float*
   if (a.strideW && a.strideW % a.ldw != 0) return fail(OG_EUNSUPPORTED, "linear_tc: strideW must be a multiple of ldw");
   if (!linear_tc_eligible(t, Whi, Wlo, a.ldw))
     return fail(OG_EUNSUPPORTED, "linear_tc: needs K >= 32, K %% 4 == 0 and 16-byte aligned rows");
-  const int64_t brows = a.strideW ? (int64_t)t.b_rows_per_batch * a.batch : a.nout;
+  // rows the B tensor map may touch: the LAST batch item only owns nout rows (a map declared over b_rows_per_batch * batch rows
+  // would let a 128-row TMA box read past the end of a head-sliced or exactly-sized operand; rows beyond the map are zero-filled)
+  const int64_t brows = a.strideW ? (int64_t)t.b_rows_per_batch * (a.batch - 1) + a.nout : a.nout;
   if (mode == 2) {                       // production kernel: persistent, chunked accumulation
     if (!linear_tc2_eligible(t, Whi, Wlo, a.ldw)) return fail(OG_EUNSUPPORTED, "linear_tc2: needs dense batches and k1 %% 32 == 0 for concat");
     return linear_tc2_launch(t, Whi, Wlo, a.ldw, brows, s);

@@ -269,3 +269,40 @@ def test_training_schedule_on_cpu_double(name):
     for k, v in model.named_buffers():
         ref = fx['buffers_after'][k]
         assert (v.double() - ref.double()).abs().max() <= 1e-6 * max(1.0, float(ref.double().abs().max())), k
+
+
+@pytest.mark.gpu
+def test_training_step_pipeline_like_the_reference_module():
+    """The reference's training_step with cached features (models/matching_module.py:71-105), every stage on the GPU library:
+    labels (generate_gt_matches) -> SuperGlue in train() mode -> criterion -> nll_weight * loss + metric_weight * metric_loss ->
+    backward -> optimiser.  The planted similarity of synthetic_pairs is the batch's ground-truth transformation."""
+    from openglue_b200 import SuperGlue, criterion, generate_gt_matches
+    from openglue_b200.synthetic import default_config, synthetic_pairs
+    dev = torch.device('cuda:0')
+    cfg = default_config(descriptor_dim=128, num_stages=2, num_iters=20)
+    cfg['precision'] = 'tf32x3'
+    model = SuperGlue(cfg)
+    model.load_state_dict(synthetic_state_dict(cfg, seed=5), strict=True)
+    model = model.to(dev).train()
+    batch = 4
+    pairs = synthetic_pairs(batch, 256, 300, 128, 1, family='planted', seed=21)
+    pairs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in pairs.items()}
+    H = torch.tensor([[0.9, 0.0, 20.0], [0.0, 0.9, 20.0], [0.0, 0.0, 1.0]], device=dev).repeat(batch, 1, 1)
+    raw = {'transformation': {'type': ['perspective'] * batch, 'H': H}, 'image0_size': pairs['image0_size'], 'image1_size': pairs['image1_size']}
+    f0 = {'keypoints': pairs['keypoints0'], 'side_info': pairs['side_info0'], 'local_descriptors': pairs['local_descriptors0']}
+    f1 = {'keypoints': pairs['keypoints1'], 'side_info': pairs['side_info1'], 'local_descriptors': pairs['local_descriptors1']}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(4):
+        data, y_true = generate_gt_matches(raw, f0, f1, 3.0, 5.0)
+        assert int((y_true['gt_matches0'] >= 0).sum()) > 0
+        y_pred = model(data)
+        loss = criterion(y_true, y_pred, margin=None)
+        total = 1.0 * loss['loss'] + 0.0 * loss['metric_loss']
+        opt.zero_grad()
+        total.backward()
+        for k, p in model.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        opt.step()
+        losses.append(float(total.detach()))
+    assert losses[-1] < losses[0], losses
