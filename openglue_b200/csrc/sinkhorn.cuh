@@ -40,6 +40,7 @@ struct SinkArgs {
   float* hist_u;                         // optional [B][iters][n+1]: u_t of every iteration  (kept for the backward pass,
   float* hist_v;                         // optional [B][iters+1][m+1]: v_t, row 0 = v_0 = 0   csrc/sinkhorn_bwd.cuh)
   int res_q16;                           // fraction (Q16) of the rows that are loaded with the L2 evict_last policy (see sink_policy)
+  int pf_rows;                           // L2 prefetch distance beyond the ring, in rows of a group (0 = off)
 };
 
 constexpr int SINK_WARPS = 8;
@@ -89,6 +90,12 @@ __device__ __forceinline__ void sink_row_copy(float* dst, const float* src, uint
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sink_smem_u32(bar)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(sink_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sink_smem_u32(bar)) : "memory");
+}
+// L2 prefetch of a row segment that the ring will ask for a few rows later: the 2-deep ring covers ~2 row times (~2 us), about the
+// loaded HBM latency (row trace: ~450 of 2400 cycles per row are spent waiting for the slot); a segment that is already in L2 when its
+// bulk copy is issued arrives in a fraction of that
+__device__ __forceinline__ void sink_row_prefetch(const float* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sink_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -170,6 +177,10 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
           ++issued;
         }
       }
+      for (int sl = SLOTS; sl < SLOTS + a.pf_rows; ++sl) {
+        const int row = r0 + grp + sl * G;
+        if (row < r1_real) sink_row_prefetch(Sb + (int64_t)row * a.lds + c0, seg_bytes);
+      }
     }
   };
   // fetch this warp's segment of row `row` into registers (float4 k = pairs 2k, 2k+1); refill the slot with the row SLOTS ahead
@@ -204,6 +215,8 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
                         (!last_sweep && keep_row(nxt)) ? pol_keep : pol_stream);
           ++issued;
         }
+        const int pfr = nxt + a.pf_rows * G;
+        if (lane == 0 && a.pf_rows > 0 && pfr < r1_real) sink_row_prefetch(Sb + (int64_t)pfr * a.lds + c0, seg_bytes);
         if (!unit_reg) {
 #pragma unroll
           for (int k = 0; k < 2 * V; ++k) {
@@ -378,6 +391,7 @@ __global__ void __launch_bounds__(SINK_WARPS * 32, (V <= 8) ? 2 : 1) sinkhorn_ke
 struct SinkPlan { int V, W, slots, occ, SP, rows_per_strip, mpad, pairs_per_launch; size_t smem; };
 constexpr int SINK_MAX_COLS = 8192;
 constexpr int SINK_L2_RESIDENT_MB = 0;   // of the 126 MB L2
+constexpr int SINK_L2_PREFETCH_ROWS = 0;
 
 template <int V, int W, int SLOTS>
 inline size_t sinkhorn_smem(int mpad) {
@@ -488,6 +502,8 @@ inline int sinkhorn_launch(const float* S, int64_t lds, int64_t strideS, const f
       const double total = (double)nb * n * (double)m * 4.0;
       const double frac = total > 0 ? std::min(1.0, res_mb * 1048576.0 / total) : 0.0;
       a.res_q16 = (int)(frac * 65536.0);
+      static const int pf = [] { const char* e = getenv("OG_SINK_PF"); return e ? atoi(e) : SINK_L2_PREFETCH_ROWS; }();
+      a.pf_rows = pf;
     }
     OG_CUDA(cudaMemsetAsync(barrier, 0, (size_t)nb * 128, stream));
     if (p.V == 8 && p.slots == 4)   rc = sinkhorn_launch_v<8, 2, 4>(a, p, stream);

@@ -41,5 +41,20 @@ for _ in range(8):
 ts.sort()
 ms = ts[len(ts) // 2]
 byts = B * (n * m * 4.0 * (iters + 1) + (n + 1) * (m + 1) * 4.0)
+def torch_reference(Sb, iters):          # superglue.py:88-111 + optimal_transport.py:4-28 in fp64 (checker for the experiment configurations)
+    import math
+    Bq, nn, mm = Sb.shape
+    Z = torch.full((Bq, nn + 1, mm + 1), 1.0, dtype=torch.float64, device=dev)
+    Z[:, :nn, :mm] = Sb.double()
+    norm = -math.log(nn + mm)
+    la = torch.full((nn + 1,), norm, dtype=torch.float64, device=dev); la[-1] += math.log(mm)
+    lb = torch.full((mm + 1,), norm, dtype=torch.float64, device=dev); lb[-1] += math.log(nn)
+    u = torch.zeros(Bq, nn + 1, dtype=torch.float64, device=dev); v = torch.zeros(Bq, mm + 1, dtype=torch.float64, device=dev)
+    for _ in range(iters):
+        u = la - torch.logsumexp(Z + v[:, None, :], 2)
+        v = lb - torch.logsumexp(Z + u[:, :, None], 1)
+    return Z + u[:, :, None] + v[:, None, :] - norm
+err = float((sc[:1].double() - torch_reference(S[:1, :, :m], iters)).abs().max())
+print('cfg=%s max |scores - fp64 reference| (pair 0) %.2e' % (os.environ.get('OG_SINK_CFG', 'default'), err), flush=True)
 print('L2_MB=%s B=%d n=%d m=%d iters=%d  ms=%.3f  GB/s=%.0f  checksum=%.6f' % (os.environ.get('OG_SINK_L2_MB', 'default'), B, n, m, iters, ms,
       byts / ms / 1e6, sc.double().sum().item()), flush=True)
