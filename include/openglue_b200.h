@@ -149,6 +149,10 @@ int og_last_forward_launches(void);
  * Both forms are parity-tested; on B200 the paired forms are ~7 % faster end to end (profiles/README.md).  Env
  * defaults: OG_GEMM_PAIR, OG_ATTN_PAIR; a negative argument leaves that setting unchanged.                                                                           */
 int og_set_tuning(int gemm_pair, int attention_pair);
+/* fuse_projections = 1 (default; env OG_FUSE_QKV): the Q / K / V projections that share their input run as one launch over the
+ * stacked weights (fp16x3 path, descriptor_dim % 128 == 0); 0: one launch per projection.  Bit-identical results (tested).
+ * Returns the previous setting; a negative argument only queries.                                                   */
+int og_set_fusion(int fuse_projections);
 
 /* ---------------------------------------------------------------------------------------------
  * Operator-level entry points (what the whole-path call is built from; tested one by one

@@ -73,6 +73,7 @@ SYMBOLS = {
     'og_attention_f16_fwd': (_I, [_P, _L, _L, _P, _P, _P, _L, _P, _P, _P, _L, _P, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I, _P]),
     'og_last_forward_launches': (_I, []),
     'og_set_tuning': (_I, [_I, _I]),
+    'og_set_fusion': (_I, [_I]),
     'og_linear_fwd': (_I, [C.POINTER(OgLinearArgs), _I, _P]),
     'og_attention_fwd': (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P]),
     'og_attention_tc_fwd': (_I, [_P, _L, _L, _P, _P, _L, _P, _P, _L, _P, _L, _L, _I, _I, _I, _I, _I, _P]),

@@ -242,6 +242,16 @@ int64_t og_workspace_bytes(const og_config* cfg, int batch, int n, int m) {
 
 int og_last_forward_launches(void) { return launch_counter(); }
 
+static int& fuse_qkv_mode() {
+  static int v = [] { const char* e = getenv("OG_FUSE_QKV"); return e ? (atoi(e) != 0) : 1; }();
+  return v;
+}
+int og_set_fusion(int fuse_projections) {
+  const int prev = fuse_qkv_mode();
+  if (fuse_projections >= 0) fuse_qkv_mode() = fuse_projections ? 1 : 0;
+  return prev;
+}
+
 int og_set_tuning(int gemm_pair, int attention_pair) {
   if (gemm_pair >= 0) linear_tc2_pair_mode() = gemm_pair ? 1 : 0;
   if (attention_pair >= 0) attention_tc_pair_mode() = attention_pair ? 1 : 0;
@@ -692,18 +702,36 @@ static int forward_impl(const og_config* cfg, const float* Wp, const float* Whi,
     return linear_f16_launch(g, W16h + woff, W16l + woff, K, g.nout, st);
   };
   struct SeqSlots { float *q, *k, *v, *o; };
+  // Q / K / V projections.  d % 128 == 0 (every shipped config): the projections that share their input run as ONE launch over the
+  // stacked weights (linear_f16.cuh OUTK 4) - Q | K | V in a self layer (same keypoints), K | V in a cross layer (+ Q on its own).
+  const int fuse_qkv = fuse_qkv_mode();
   auto project_f16 = [&](int l, int qrow0, int nq_rows, int srow0, int ns, int sbatch, float* aq0, float* aq1, float* as0, float* as1,
                          SeqSlots& ss) -> int {
     int r;
     ss.q = new_slot(); ss.k = new_slot(); ss.v = new_slot(); ss.o = new_slot();
-    F16LinearArgs gq = gemm16(w.x + (int64_t)qrow0 * d, d, d, nullptr, 0, 0, L.qkv_w[l], Wp + L.qkv_b[l], nq_rows, d, aq0, aq1, nullptr, M16(l, 0));
-    gq.Y = w.q + (int64_t)qrow0 * d; gq.ldy = d; gq.amax_out = ss.q;
-    if ((r = run16(gq, L.qkv_w[l])) != OG_OK) return r;
+    const int64_t ldv = (srow0 == 0) ? w.ldn : w.ldm;
+    const int64_t voff = (srow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
+    const bool fuse = fuse_qkv && d % tcf::BN == 0;
+    const bool same_src = qrow0 == srow0 && nq_rows == sbatch * ns;
+    if (!(fuse && same_src)) {
+      F16LinearArgs gq = gemm16(w.x + (int64_t)qrow0 * d, d, d, nullptr, 0, 0, L.qkv_w[l], Wp + L.qkv_b[l], nq_rows, d, aq0, aq1, nullptr, M16(l, 0));
+      gq.Y = w.q + (int64_t)qrow0 * d; gq.ldy = d; gq.amax_out = ss.q;
+      if ((r = run16(gq, L.qkv_w[l])) != OG_OK) return r;
+    }
+    if (fuse) {
+      const int k0 = same_src ? 0 : 1, nk_ = 3 - k0;
+      F16LinearArgs g = gemm16(w.x + (int64_t)srow0 * d, d, d, nullptr, 0, 0, 0, Wp + L.qkv_b[l] + k0 * d, ns, nk_ * d, as0, as1, nullptr, M16(l, k0));
+      g.batch = sbatch; g.strideA = (int64_t)ns * d;
+      g.nkinds = nk_; g.kind0 = k0; g.kind_cols = d;
+      g.ldy = d; g.strideY = (int64_t)ns * d;
+      if (k0 == 0) { g.Y = w.q + (int64_t)srow0 * d; g.amax_out = ss.q; }
+      g.Yh = kh16 + (int64_t)srow0 * d; g.Yl = kl16 + (int64_t)srow0 * d; g.scale_out = ss.k;
+      g.Yth = vth16 + voff; g.Ytl = vtl16 + voff; g.ldyt = ldv; g.strideYt = (int64_t)d * ldv; g.scale_out_v = ss.v;
+      return run16(g, L.qkv_w[l] + (int64_t)k0 * d * d);
+    }
     F16LinearArgs gk = gemm16(w.x + (int64_t)srow0 * d, d, d, nullptr, 0, 0, 0, Wp + L.qkv_b[l] + d, sbatch * ns, d, as0, as1, nullptr, M16(l, 1));
     gk.Yh = kh16 + (int64_t)srow0 * d; gk.Yl = kl16 + (int64_t)srow0 * d; gk.ldy = d; gk.scale_out = ss.k;
     if ((r = run16(gk, L.qkv_w[l] + (int64_t)d * d)) != OG_OK) return r;
-    const int64_t ldv = (srow0 == 0) ? w.ldn : w.ldm;
-    const int64_t voff = (srow0 == 0) ? 0 : (int64_t)B * d * w.ldn;
     F16LinearArgs gv = gemm16(w.x + (int64_t)srow0 * d, d, d, nullptr, 0, 0, 0, Wp + L.qkv_b[l] + 2 * d, ns, d, as0, as1, nullptr, M16(l, 2));
     gv.batch = sbatch; gv.strideA = (int64_t)ns * d; gv.Yth = vth16 + voff; gv.Ytl = vtl16 + voff; gv.ldyt = ldv; gv.strideYt = (int64_t)d * ldv;
     gv.scale_out = ss.v;
@@ -926,7 +954,7 @@ int og_linear_f16_fwd(const og_linear_args* a, const void* Wh16, const void* Wl1
   const __half* bh = static_cast<const __half*>(Wh16); const __half* bl = static_cast<const __half*>(Wl16);
   if (!linear_f16_eligible(g, bh, bl, a->ldw))
     return fail(OG_EUNSUPPORTED, "linear_f16: needs K >= 64, 16-byte aligned rows, exactly one output kind (Y | Yh,Yl | Yth,Ytl)");
-  const int64_t brows = a->strideW ? (int64_t)g.b_rows_per_batch * a->batch : a->nout;
+  const int64_t brows = a->strideW ? (int64_t)g.b_rows_per_batch * (a->batch - 1) + a->nout : a->nout;
   return linear_f16_launch(g, bh, bl, a->ldw, brows, (cudaStream_t)stream);
 }
 

@@ -19,6 +19,10 @@
 // OUTK: 1 = fp32 Y through TMA (bias / ReLU, residual through TMA with RTMA, amax tracking)
 //       2 = row-major fp16 hi / lo through TMA (K operand of the attention kernel)
 //       3 = transposed fp16 hi / lo, direct stores (V^T operand)
+//       4 = SEVERAL projections of the same A in one launch (Q | K | V or K | V): B = the stacked weights, the output kind of a
+//           tile follows from its column block (kind = kind0 + n0 / kind_cols: 0 -> as OUTK 1, 1 -> as OUTK 2, 2 -> as OUTK 3), every
+//           kind with its own weight scale / norm bound (w_meta + 4 per kind).  Same tiles, same arithmetic as the separate launches
+//           (results are bit-identical); one launch instead of three, and 2 - 3 x the tiles per launch (shorter tail).
 #pragma once
 #include "tc_common.cuh"
 #include "linear_tc2.cuh"   // linear_tc2_pair_mode (og_set_tuning / OG_GEMM_PAIR is shared by both forms)
@@ -45,6 +49,8 @@ struct F16LinearArgs {
   float* amax_out;                      // optional: max |Y| (atomicMax; zeroed by the caller)
   float* scale_out;                     // OUTK 2 / 3: receives the scale the fp16 outputs were written with
   int swap_halves;                      // debug: pack A with element 2c in the HIGH half (probe of the TMEM operand layout)
+  int nkinds, kind0, kind_cols;         // OUTK 4 (nkinds > 1): output kinds kind0 .. kind0 + nkinds - 1, kind_cols columns each (multiple of 128)
+  float* scale_out_v;                   // OUTK 4: scale of the transposed (kind 2) output; scale_out is the row-major (kind 1) one
 };
 
 namespace tcf {
@@ -137,9 +143,17 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
   const float s_w = __ldg(a.w_meta);
   const float alpha_eff = a.alpha / (s_a * s_w);             // exact: both scales are powers of two
   float s_out_scale = 1.f;
-  if (OUTK != 1) {
+  if (OUTK == 2 || OUTK == 3) {
     s_out_scale = f16_scale_for(fabsf(a.alpha) * fmaf(amax_a, __ldg(a.w_meta + 1), __ldg(a.w_meta + 2)));
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.scale_out) *a.scale_out = s_out_scale;
+  }
+  if (OUTK == 4 && blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int kk = 0; kk < a.nkinds; ++kk) {
+      const float* wm = a.w_meta + 4 * kk;
+      const float so = f16_scale_for(fabsf(a.alpha) * fmaf(amax_a, __ldg(wm + 1), __ldg(wm + 2)));
+      if (a.kind0 + kk == 1 && a.scale_out) *a.scale_out = so;
+      if (a.kind0 + kk == 2 && a.scale_out_v) *a.scale_out_v = so;
+    }
   }
 
   auto arrive_leader = [&](uint64_t* bar) {
@@ -331,22 +345,32 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
       if (warp == 0 && lane == 0) OG_TRACE_EVT(8, ntile);
       const int grow = m0 + trow;
       const bool row_ok = grow < a.rows;
+      // output kind of this tile, its column origin inside that output tensor, and the kind's operand scales
+      int okind = OUTK, kidx = 0, ocols = a.nout;
+      float alpha_t = alpha_eff, sos = s_out_scale;
+      if (OUTK == 4) {
+        kidx = n0 / a.kind_cols; okind = a.kind0 + kidx + 1; ocols = a.kind_cols;
+        const float* wm = a.w_meta + 4 * kidx;
+        alpha_t = a.alpha / (s_a * __ldg(wm));
+        if (okind != 1) sos = f16_scale_for(fabsf(a.alpha) * fmaf(amax_a, __ldg(wm + 1), __ldg(wm + 2)));
+      }
       if (wg_tid == 0 && !r_tma && OUTK != 3) tma_store_wait_read<0>();   // the previous tile's stores have read the staging buffers
       asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");       // ... and the staged bias is visible
-      const int cl0 = half * HN, cb0 = n0 + cl0;               // first column of this warpgroup's half (tile / global)
+      const int cl0 = half * HN, cb0 = n0 + cl0;               // first column of this warpgroup's half (tile / stacked B rows)
+      const int ob0 = cb0 - kidx * ocols;                      // ... inside its output tensor
       if (cb0 < a.nout) {                                      // uniform across the warpgroup
         float y[HN];
 #pragma unroll
         for (int j = 0; j < HN; j += 4) {
           const float4 bv = *reinterpret_cast<const float4*>(&bars->bias[pb][cl0 + j]);
-          y[j] = fmaf(racc[j], alpha_eff, bv.x);         y[j + 1] = fmaf(racc[j + 1], alpha_eff, bv.y);
-          y[j + 2] = fmaf(racc[j + 2], alpha_eff, bv.z); y[j + 3] = fmaf(racc[j + 3], alpha_eff, bv.w);
+          y[j] = fmaf(racc[j], alpha_t, bv.x);         y[j + 1] = fmaf(racc[j + 1], alpha_t, bv.y);
+          y[j + 2] = fmaf(racc[j + 2], alpha_t, bv.z); y[j + 3] = fmaf(racc[j + 3], alpha_t, bv.w);
         }
         if (a.relu) {
 #pragma unroll
           for (int j = 0; j < HN; ++j) y[j] = fmaxf(y[j], 0.f);
         }
-        if constexpr (OUTK == 1) {
+        if (okind == 1) {
           if (r_tma) mbar_wait(&bars->r_full[half], ntile & 1);
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {                     // two 32-column fp32 chunks, each staged in its own buffer
@@ -357,51 +381,48 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
               float4* cell = reinterpret_cast<float4*>(buf + ((c4 ^ (trow & 7)) * 16));
               if (r_tma) { const float4 r = *cell; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
               *cell = o;
-              if (a.amax_out && row_ok) {
-                const int cg = cb0 + cc * 32 + 4 * c4;         // columns beyond nout hold alpha * 0 + 0 = 0: harmless for a max
-                (void)cg;
+              if (a.amax_out && row_ok)                        // columns beyond nout hold alpha * 0 + 0 = 0: harmless for a max
                 tmax = fmaxf(tmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-              }
             }
           }
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
           if (wg_tid == 0) {
-            tma_store_3d(&map_y, s_out + (half * 2 + 0) * OUT_TILE, cb0, m0, bz);
-            if (cb0 + 32 < a.nout) tma_store_3d(&map_y, s_out + (half * 2 + 1) * OUT_TILE, cb0 + 32, m0, bz);
+            tma_store_3d(&map_y, s_out + (half * 2 + 0) * OUT_TILE, ob0, m0, bz);
+            if (ob0 + 32 < ocols) tma_store_3d(&map_y, s_out + (half * 2 + 1) * OUT_TILE, ob0 + 32, m0, bz);
             tma_store_commit();
           }
-        } else if constexpr (OUTK == 2) {
+        } else if (okind == 2) {
           uint8_t* bh = s_out + (half * 2 + 0) * OUT_TILE + trow * 128;      // hi row: 64 halves = 128 bytes
           uint8_t* bl = s_out + (half * 2 + 1) * OUT_TILE + trow * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                        // 16-byte chunk c = columns 8c .. 8c+7
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_f16x2(y[8 * c + 2 * e] * s_out_scale, y[8 * c + 2 * e + 1] * s_out_scale, h[e], l[e]);
+            for (int e = 0; e < 4; ++e) split_f16x2(y[8 * c + 2 * e] * sos, y[8 * c + 2 * e + 1] * sos, h[e], l[e]);
             *reinterpret_cast<uint4*>(bh + ((c ^ (trow & 7)) * 16)) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(bl + ((c ^ (trow & 7)) * 16)) = make_uint4(l[0], l[1], l[2], l[3]);
           }
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
           if (wg_tid == 0) {
-            tma_store_3d(&map_yh, s_out + (half * 2 + 0) * OUT_TILE, cb0, m0, bz);
-            tma_store_3d(&map_yl, s_out + (half * 2 + 1) * OUT_TILE, cb0, m0, bz);
+            tma_store_3d(&map_yh, s_out + (half * 2 + 0) * OUT_TILE, ob0, m0, bz);
+            tma_store_3d(&map_yl, s_out + (half * 2 + 1) * OUT_TILE, ob0, m0, bz);
             tma_store_commit();
           }
-        } else {                                               // OUTK == 3: for a fixed column the 32 lanes write 32 consecutive rows
+        } else {                                               // kind 3: for a fixed column the 32 lanes write 32 consecutive rows
           if (row_ok) {
             const int64_t ytoff = (int64_t)bz * a.strideYt + grow;
 #pragma unroll
             for (int j = 0; j < HN; j += 2) {
               uint32_t h, l;
-              split_f16x2(y[j] * s_out_scale, y[j + 1] * s_out_scale, h, l);
-              if (cb0 + j < a.nout) {
-                const int64_t o = ytoff + (int64_t)(cb0 + j) * a.ldyt;
+              split_f16x2(y[j] * sos, y[j + 1] * sos, h, l);
+              if (ob0 + j < ocols) {
+                const int64_t o = ytoff + (int64_t)(ob0 + j) * a.ldyt;
                 a.Yth[o] = __ushort_as_half((unsigned short)(h & 0xffffu)); a.Ytl[o] = __ushort_as_half((unsigned short)(l & 0xffffu));
               }
-              if (cb0 + j + 1 < a.nout) {
-                const int64_t o = ytoff + (int64_t)(cb0 + j + 1) * a.ldyt;
+              if (ob0 + j + 1 < ocols) {
+                const int64_t o = ytoff + (int64_t)(ob0 + j + 1) * a.ldyt;
                 a.Yth[o] = __ushort_as_half((unsigned short)(h >> 16)); a.Ytl[o] = __ushort_as_half((unsigned short)(l >> 16));
               }
             }
@@ -410,7 +431,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
       }
       if (warp == 0 && lane == 0) OG_TRACE_EVT(9, ntile);
     }
-    if (OUTK == 1 && a.amax_out) {
+    if ((OUTK == 1 || OUTK == 4) && a.amax_out) {
       tmax = warp_max(tmax);
       if (lane == 0 && tmax > 0.f) atomic_amax(a.amax_out, tmax);
     }
@@ -430,11 +451,15 @@ inline bool linear_f16_eligible(const F16LinearArgs& a, const __half* Bh, const 
   if (a.A2 && (a.k1 % 64 != 0 || a.lda2 % 4 != 0 || !al16(a.A2) || (a.batch > 1 && a.strideA2 != (int64_t)a.rows * a.lda2))) return false;
   if (!a.w_meta || !(a.amax_in[0] || a.amax_in[1] || a.amax_in[2])) return false;
   const int kinds = (a.Y ? 1 : 0) + (a.Yh ? 1 : 0) + (a.Yth ? 1 : 0);
-  if (kinds != 1) return false;
+  if (a.nkinds > 1) {                                       // stacked projections: kinds kind0 .. kind0 + nkinds - 1, one output each
+    if (a.kind0 < 0 || a.kind0 + a.nkinds > 3 || kinds != a.nkinds || a.kind_cols % tcf::BN != 0 || a.nout != a.nkinds * a.kind_cols) return false;
+    if ((a.kind0 == 0) != (a.Y != nullptr) || !a.Yh || (a.kind0 + a.nkinds == 3) != (a.Yth != nullptr) || a.R || a.relu) return false;
+    if (a.Yth && !a.scale_out_v) return false;
+  } else if (kinds != 1) return false;
   if (a.Y && !(a.ldy % 4 == 0 && a.strideY % 4 == 0 && al16(a.Y))) return false;
   if (a.Y && a.R && !(a.ldr % 4 == 0 && a.strideR % 4 == 0 && al16(a.R) && a.nout % 32 == 0)) return false;
   if (a.Yh && !(a.Yl && a.ldy % 8 == 0 && a.strideY % 8 == 0 && al16(a.Yh) && al16(a.Yl) && !a.R && a.scale_out)) return false;
-  if (a.Yth && !(a.Ytl && !a.R && a.scale_out)) return false;
+  if (a.Yth && !(a.Ytl && !a.R && (a.scale_out || a.scale_out_v))) return false;
   return true;
 }
 
@@ -454,20 +479,21 @@ inline int linear_f16_launch_t(const F16LinearArgs& a, const __half* Bh, const _
   if ((rc = tc::make_tmap_2d_f16(&mh, Bh, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, C::BROWS)) != OG_OK) return rc;
   if ((rc = tc::make_tmap_2d_f16(&ml, Bl, (uint64_t)b_total_rows, (uint64_t)K, (uint64_t)ldb, C::BROWS)) != OG_OK) return rc;
   CUtensorMap my = ma, myh = ma, myl = ma, mr = ma;
-  if (a.Y && (rc = tc::make_tmap_3d(&my, a.Y, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
-  if (a.Yh && (rc = tc::make_tmap_3d_f16(&myh, a.Yh, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
-  if (a.Yh && (rc = tc::make_tmap_3d_f16(&myl, a.Yl, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+  const int ocols = a.nkinds > 1 ? a.kind_cols : a.nout;     // columns of ONE output tensor
+  if (a.Y && (rc = tc::make_tmap_3d(&my, a.Y, a.batch, a.rows, ocols, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+  if (a.Yh && (rc = tc::make_tmap_3d_f16(&myh, a.Yh, a.batch, a.rows, ocols, a.ldy, a.strideY, BM)) != OG_OK) return rc;
+  if (a.Yh && (rc = tc::make_tmap_3d_f16(&myl, a.Yl, a.batch, a.rows, ocols, a.ldy, a.strideY, BM)) != OG_OK) return rc;
   const int r_tma = a.Y && a.R;
   if (r_tma && (rc = tc::make_tmap_3d(&mr, a.R, a.batch, a.rows, a.nout, a.ldr, a.strideR, BM)) != OG_OK) return rc;
   using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                         F16LinearArgs, Sched);
-  static const Kern kerns[4] = {linear_f16_kernel<PAIR, 0, 1>, linear_f16_kernel<PAIR, 1, 1>, linear_f16_kernel<PAIR, 0, 2>,
-                                linear_f16_kernel<PAIR, 0, 3>};
+  static const Kern kerns[5] = {linear_f16_kernel<PAIR, 0, 1>, linear_f16_kernel<PAIR, 1, 1>, linear_f16_kernel<PAIR, 0, 2>,
+                                linear_f16_kernel<PAIR, 0, 3>, linear_f16_kernel<PAIR, 0, 4>};
   static DeviceFlags attr_set;
   if (attr_set.once()) {
     for (Kern k : kerns) OG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
-  const Kern kern = a.Y ? (r_tma ? kerns[1] : kerns[0]) : (a.Yh ? kerns[2] : kerns[3]);
+  const Kern kern = a.nkinds > 1 ? kerns[4] : a.Y ? (r_tma ? kerns[1] : kerns[0]) : (a.Yh ? kerns[2] : kerns[3]);
   Sched sc;
   sc.ntmg = cdiv(cdiv(a.rows, BM), NC); sc.ntn = cdiv(a.nout, BN); sc.ngroups = sc.ntmg * sc.ntn * a.batch;
   sc.nkb = cdiv(K, BK); sc.nchunks = cdiv(sc.nkb, CHUNK_KB);

@@ -437,9 +437,10 @@ inline int linear_tc2_launch_t(const TcLinearArgs& a, const float* Bhi, const fl
     if (a.Yhi && (rc = tc::make_tmap_3d(&myh, a.Yhi, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
     if (a.Yhi && (rc = tc::make_tmap_3d(&myl, a.Ylo, a.batch, a.rows, a.nout, a.ldy, a.strideY, BM)) != OG_OK) return rc;
   }
-  // residual through TMA as well: needs the staging buffers for itself, so only without split outputs
+  // residual through TMA as well: needs the staging buffers for itself, so only without split outputs; the specialised
+  // instantiation writes Y only (a transposed output - the context descriptors of image 0 - takes the generic one)
   CUtensorMap mr = ma;
-  const int r_tma = y_tma && a.R && a.Y && !a.Yhi && a.ldr % 4 == 0 && a.strideR % 4 == 0 && al16(a.R) && a.nout % 32 == 0;
+  const int r_tma = y_tma && a.R && a.Y && !a.Yhi && !a.Yt && !a.Ythi && a.ldr % 4 == 0 && a.strideR % 4 == 0 && al16(a.R) && a.nout % 32 == 0;
   if (r_tma && (rc = tc::make_tmap_3d(&mr, a.R, a.batch, a.rows, a.nout, a.ldr, a.strideR, BM)) != OG_OK) return rc;
   // epilogue specialisation (see the kernel's OUTK): everything else takes the generic instantiation
   int outk = 0;

@@ -164,3 +164,37 @@ def test_attention_f16_operator(B, H, nq, nk, pair):
     print(f'\n[attention_f16 B{B} H{H} {nq}x{nk} pair={pair}] rel err {err:.2e}')
     assert err <= 5e-6
     assert float(oamax) == float(out.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('batch,n,m', [(2, 330, 197), (1, 256, 256), (3, 64, 1)])
+def test_fused_projections_are_bit_identical(batch, n, m):
+    """One launch over the stacked Q | K | V (self) or K | V (cross) weights (linear_f16.cuh OUTK 4) computes the same tiles with the
+    same arithmetic as one launch per projection: the whole path's outputs must not change by a single bit."""
+    import torch
+    from openglue_b200 import SuperGlue, _cabi
+    from openglue_b200.synthetic import default_config, synthetic_pairs, synthetic_state_dict
+    dev = torch.device('cuda:0')
+    cfg = default_config(descriptor_dim=256, num_stages=2, num_iters=10)
+    cfg['precision'] = 'fp16x3'
+    model = SuperGlue(cfg)
+    model.load_state_dict(synthetic_state_dict(cfg, seed=8), strict=True)
+    model = model.to(dev).eval()
+    data = synthetic_pairs(batch, n, m, 256, 1, family='planted', seed=31)
+    data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    lib = _cabi.lib()
+    prev = lib.og_set_fusion(1)
+    try:
+        with torch.no_grad():
+            fused = {k: v.clone() for k, v in model(data).items()}
+            n_fused = model.last_launches
+            lib.og_set_fusion(0)
+            plain = {k: v.clone() for k, v in model(data).items()}
+            n_plain = model.last_launches
+    finally:
+        lib.og_set_fusion(prev)
+    for k in fused:
+        assert torch.equal(fused[k], plain[k]), k
+    stages = cfg['attention_gnn']['num_stages']
+    same = 2 if n != m else 1                                  # self layers: one launch per image when n != m
+    assert n_plain - n_fused == stages * (2 * same + 2 * 1)     # self: Q,K,V -> 1 (2 saved per call); cross: K,V -> 1 (1 saved per call, 2 calls)

@@ -193,6 +193,14 @@ def test_forward_matches_oracle(batch, n, m, kw, family, precision):
     res = MatchingCore(model, 0.2)(_to_dev(data), want_scores=True)
     assert (res['scores'].cpu().double() - ref64['scores']).abs().max() <= bound
     check_matches(res, ref, ref64['scores'], bound)
+    # context descriptors (superglue.py:66-69), written into POISONED buffers (an output the kernels skip must not pass by luck)
+    poison = [torch.full((batch, cfg['descriptor_dim'], k), float('nan'), device=DEV) for k in (n, m)]
+    del poison
+    out = model(_to_dev(data))
+    for i in (0, 1):
+        c = out[f'context_descriptors{i}'].cpu().double()
+        assert torch.isfinite(c).all()
+        assert (c - ref64[f'context_descriptors{i}']).abs().max() <= 1e-4 * max(1.0, float(ref64[f'context_descriptors{i}'].abs().max()))
     # matches1 (inference.py:176-190): same decisive rule, seen from image 1
     row_ok, col_ok = decisive_rows(ref64['scores'], 2 * bound)
     i1 = ref64['scores'][:, :-1, :-1].argmax(1)
