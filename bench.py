@@ -481,8 +481,8 @@ def main():
             dist.destroy_process_group()
         return
     traffic = {}
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath) and args.workload == 'C3' and batch == 16 and args.precision == 'tf32x3':     # (tf32 kernels only)
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    if os.path.exists(tpath) and args.workload == 'C3' and batch == 16 and args.precision != 'fp32':
         traffic = json.load(open(tpath))     # ncu dram bytes per launch, captured at exactly these shapes
     fl = flops_per_pair(n, m, d, stages, s_dim)
     line = {
@@ -505,7 +505,9 @@ def main():
         'roofline': {'kernel': 'fused attention (self layer: %d sequences x %d heads, %d x %d, Dh=%d)' % (nb, H, n, n, d // H),
                      'bound': 'tensor', 'achieved': attn_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                      'frac': attn_tflops / peaks['bf16_tflops'],
-                     'traffic': traffic.get('attention_tc_self_32seq_2048', {}).get('bytes'), 'peak_source': peaks['source'] + ' bf16 burst',
+                     'traffic': traffic.get('attention_f16_self_32seq_2048' if (args.precision == 'fp16x3' and d // H == 64)
+                                            else 'attention_tc_self_32seq_2048', {}).get('bytes') if args.workload == 'C3' else None,
+                     'peak_source': peaks['source'] + ' bf16 burst',
                      'ms_per_launch': ms_attn, 'flops_per_launch': attn_flops,
                      # the kernel runs 3 MMAs per algorithmic product (fp32-grade accuracy is part of the contract): its own ceiling
                      # is bf16_peak / 6 with tf32 operands (half rate) and bf16_peak / 3 with fp16 operands
@@ -514,7 +516,8 @@ def main():
         'roofline_sinkhorn': {'kernel': 'sinkhorn (%d pairs, %d iterations, one launch)' % (batch, iters), 'bound': 'hbm',
                               'achieved': sink_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                               'frac': sink_gbs / peaks['hbm_gbs'],
-                              'traffic': traffic.get('sinkhorn_16pairs_2048_100it', {}).get('bytes'), 'peak_source': peaks['source'],
+                              'traffic': traffic.get('sinkhorn_16pairs_2048_100it', {}).get('bytes') if args.workload == 'C3' else None,
+                              'peak_source': peaks['source'],
                               'ms_per_launch': ms_sink, 'bytes_per_launch': sinkhorn_bytes_per_pair(n, m, iters) * batch},
         'flops_per_pair': fl['total'],
         'end_to_end_tensor_frac': value / world * fl['total'] / (peaks['bf16_tflops_sustained'] * 1e12),
