@@ -363,6 +363,31 @@ int og_mix_param_grad(const float* colsum, const float* mix, float* dmix, int d,
 int og_kenc_input(const float* kpts, const float* side, int rows, int side_info_size, float width, float height,
                   float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SuperPoint front-end operators: SuperPointNet.forward (models/features/superpoint/model.py:61-129)
+ * on NHWC activations.  Convolutions = og_sp_im2col3x3 (3x3, pad 1) + og_linear_auto_fwd (bias / ReLU fused; 1x1: the GEMM alone).
+ *   og_sp_im2col3x3     out[p, (3 ky + kx) C + c] = x[b, y + ky - 1, x + kx - 1, c] (zero padding);  x [B,H,W,C], out [B H W, 9 C]
+ *   og_sp_maxpool2x2    nn.MaxPool2d(2, 2) on NHWC
+ *   og_row_normalize    mode 0: x /= ||x||_2 per row (model.py:70-71);  mode 1: F.normalize (x /= max(||x||_2, eps))
+ *   og_sp_heat_nms      probs [B,Hc,Wc,65] (channel softmax done) -> heat [B, 8 Hc, 8 Wc]: pixel shuffle (model.py:84-86), nms2d
+ *                       (kornia >= 0.6.1, restated: x > max(0, the other k*k - 1 values of the replicate-padded window)),
+ *                       F.threshold + nonzero (model.py:89-92) and remove_borders (utils.py:4-11): the score where kept, else 0
+ *   og_sp_compact       per image: surviving pixels in row-major order (torch.nonzero) -> cand_idx / cand_score [B, cap], count [B]
+ *   og_sp_select        per image: n_out[b] keypoints, mode[b] = 0 in candidate order | 1 = the largest scores, descending (torch.topk,
+ *                       equal scores: lower index first; top_k_keypoints utils.py:34-39, min_stack models/features/utils.py:28-56);
+ *                       kpts [B,out_cap,2] as (x, y) floats, scores [B,out_cap];  max_count = the largest count (<= 16384)
+ *   og_sp_sample_desc   sample_desc_from_points (utils.py:14-31): bilinear grid_sample (align_corners False) of the coarse descriptors
+ *                       [B,Hc,Wc,D] at the keypoints + F.normalize -> desc [B,out_cap,D]                                        */
+int og_sp_im2col3x3(const float* x, int B, int H, int W, int C, float* out, void* stream);
+int og_sp_maxpool2x2(const float* x, int B, int H, int W, int C, float* out, void* stream);
+int og_row_normalize(float* x, int64_t rows, int C, int mode, float eps, void* stream);
+int og_sp_heat_nms(const float* probs, int B, int Hc, int Wc, int nms_kernel, float threshold, int border, float* heat, void* stream);
+int og_sp_compact(const float* heat, int B, int HW, int cap, int* cand_idx, float* cand_score, int* count, void* stream);
+int og_sp_select(const int* cand_idx, const float* cand_score, const int* count, const int* n_out, const int* mode, int B, int cap, int W,
+                 int out_cap, int max_count, float* kpts, float* scores, void* stream);
+int og_sp_sample_desc(const float* coarse, int B, int Hc, int Wc, int D, const float* kpts, const int* n_out, int out_cap, int max_n, int cell,
+                      float* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

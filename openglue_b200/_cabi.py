@@ -105,6 +105,14 @@ SYMBOLS = {
     'og_mix_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P]),
     'og_mix_param_grad': (_I, [_P, _P, _P, _I, _P]),
     'og_kenc_input': (_I, [_P, _P, _I, _I, _F, _F, _P, _P]),
+    # SuperPoint front-end operators (row f4)
+    'og_sp_im2col3x3': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'og_sp_maxpool2x2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'og_row_normalize': (_I, [_P, _L, _I, _I, _F, _P]),
+    'og_sp_heat_nms': (_I, [_P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    'og_sp_compact': (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    'og_sp_select': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'og_sp_sample_desc': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

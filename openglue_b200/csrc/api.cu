@@ -17,6 +17,7 @@
 #include "criterion.cuh"
 #include "collate.cuh"
 #include "train_ops.cuh"
+#include "superpoint.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -546,6 +547,68 @@ int og_kenc_input(const float* kpts, const float* side, int rows, int side_info_
   OG_CHECK_ARG(kpts && out && rows > 0 && side_info_size >= 0 && (side_info_size == 0 || side), "kenc_input: bad arguments");
   kenc_input_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(kpts, side, rows, side_info_size, width - 1.f, height - 1.f, out);
   OG_LAUNCH_CHECK("kenc_input_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
+// ---- SuperPoint front-end operators (row f4; csrc/superpoint.cuh) ----
+int og_sp_im2col3x3(const float* x, int B, int H, int W, int C, float* out, void* stream) {
+  OG_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && C > 0, "sp_im2col3x3: bad arguments");
+  im2col3x3_kernel<<<sp_grid((int64_t)B * H * W * 9 * ((C % 4 == 0) ? C / 4 : C)), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
+  OG_LAUNCH_CHECK("im2col3x3_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_sp_maxpool2x2(const float* x, int B, int H, int W, int C, float* out, void* stream) {
+  OG_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "sp_maxpool2x2: bad arguments");
+  maxpool2x2_kernel<<<sp_grid((int64_t)B * (H / 2) * (W / 2) * C), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out);
+  OG_LAUNCH_CHECK("maxpool2x2_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_row_normalize(float* x, int64_t rows, int C, int mode, float eps, void* stream) {
+  OG_CHECK_ARG(x && rows >= 0 && C > 0 && (mode == 0 || mode == 1), "row_normalize: bad arguments");
+  if (rows == 0) return OG_OK;
+  row_normalize_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, C, mode, eps);
+  OG_LAUNCH_CHECK("row_normalize_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_sp_heat_nms(const float* probs, int B, int Hc, int Wc, int nms_kernel, float threshold, int border, float* heat, void* stream) {
+  OG_CHECK_ARG(probs && heat && B > 0 && Hc > 0 && Wc > 0 && nms_kernel > 0 && nms_kernel % 2 == 1 && border >= 0, "sp_heat_nms: bad arguments");
+  sp_heat_nms_kernel<<<sp_grid((int64_t)B * Hc * Wc * 64), 256, 0, (cudaStream_t)stream>>>(probs, B, Hc, Wc, nms_kernel, threshold, border, heat);
+  OG_LAUNCH_CHECK("sp_heat_nms_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_sp_compact(const float* heat, int B, int HW, int cap, int* cand_idx, float* cand_score, int* count, void* stream) {
+  OG_CHECK_ARG(heat && cand_idx && cand_score && count && B > 0 && HW > 0 && cap > 0, "sp_compact: bad arguments");
+  sp_compact_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(heat, HW, cap, cand_idx, cand_score, count);
+  OG_LAUNCH_CHECK("sp_compact_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_sp_select(const int* cand_idx, const float* cand_score, const int* count, const int* n_out, const int* mode, int B, int cap, int W,
+                 int out_cap, int max_count, float* kpts, float* scores, void* stream) {
+  OG_CHECK_ARG(cand_idx && cand_score && count && n_out && mode && kpts && scores, "sp_select: null pointer");
+  OG_CHECK_ARG(B > 0 && cap > 0 && W > 0 && out_cap > 0 && max_count >= 0, "sp_select: bad sizes");
+  if (max_count > SP_MAX_CAND) return fail(OG_EUNSUPPORTED, "sp_select: %d candidates in one image exceed the sort capacity %d", max_count, SP_MAX_CAND);
+  int n2 = 1;
+  while (n2 < max_count) n2 <<= 1;
+  const int smem = 2 * n2 * 4;
+  static DeviceFlags attr_set;
+  if (attr_set.once()) OG_CUDA(cudaFuncSetAttribute(sp_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SP_MAX_CAND * 4));
+  sp_select_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(cand_idx, cand_score, count, n_out, mode, cap, W, out_cap, kpts, scores);
+  OG_LAUNCH_CHECK("sp_select_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+int og_sp_sample_desc(const float* coarse, int B, int Hc, int Wc, int D, const float* kpts, const int* n_out, int out_cap, int max_n, int cell,
+                      float* desc, void* stream) {
+  OG_CHECK_ARG(coarse && kpts && n_out && desc && B > 0 && Hc > 0 && Wc > 0 && D > 0 && out_cap > 0 && cell > 0, "sp_sample_desc: bad arguments");
+  if (max_n <= 0) return OG_OK;
+  sp_sample_desc_kernel<<<dim3(cdiv(max_n, 8), B), 256, 0, (cudaStream_t)stream>>>(coarse, Hc, Wc, D, kpts, n_out, out_cap, cell, desc);
+  OG_LAUNCH_CHECK("sp_sample_desc_kernel");
   launch_counter()++;
   return OG_OK;
 }

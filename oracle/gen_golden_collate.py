@@ -40,7 +40,9 @@ def synthetic_items(case):
             lafs[:, 0, 2] = torch.rand(c, generator=g) * (W - 1)          # x
             lafs[:, 1, 2] = torch.rand(c, generator=g) * (H - 1)          # y
             it[f'lafs{i}'] = lafs
-            it[f'scores{i}'] = torch.rand(c, generator=g)                  # distinct with probability 1: topk order is unambiguous
+            # DISTINCT scores (torch.rand has 24-bit resolution: 5000 draws collide with probability ~0.5, and torch.topk does not
+            # define the order of equal scores): a random permutation of c levels + a jitter smaller than the level spacing
+            it[f'scores{i}'] = (torch.randperm(c, generator=g).float() + 0.5 * torch.rand(c, generator=g)) / c
             it[f'descriptors{i}'] = torch.randn(c, d, generator=g)
         it['transformation'] = {'type': '3d_reprojection', 'K0': torch.randn(3, 3, generator=g), 'K1': torch.randn(3, 3, generator=g),
                                 'R': torch.randn(3, 3, generator=g), 'T': torch.randn(3, generator=g),

@@ -1,0 +1,104 @@
+"""SuperPoint front-end against fixtures minted from the UNMODIFIED reference module
+(oracle/gen_golden_superpoint.py; kornia's nms2d restated there - kornia is not installed)."""
+import os
+
+import pytest
+import torch
+
+CASES = ['superpoint_all', 'superpoint_topk', 'superpoint_thr']
+
+
+def _load(name):
+    here = os.path.dirname(os.path.abspath(__file__))
+    return torch.load(os.path.join(here, 'golden', name + '.pt'), weights_only=False)
+
+
+def _decisions(heat, nms, thr, border, margin):
+    """From a dense score map: which pixels the reference keeps (keep) and which of these decisions are DECISIVE - no comparison of
+    the rule (x > every other value of the replicate-padded window, x > 0, x > thr) is closer than `margin`."""
+    import torch.nn.functional as F
+    B, H, W = heat.shape
+    r = nms // 2
+    xp = F.pad(heat[:, None], [r, r, r, r], mode='replicate')
+    win = xp.unfold(2, nms, 1).unfold(3, nms, 1).reshape(B, H, W, nms * nms)
+    others = torch.cat([win[..., :nms * nms // 2], win[..., nms * nms // 2 + 1:]], -1)
+    mx = others.max(-1).values.clamp_min(0)
+    gap = (heat - mx)
+    keep = (gap > 0) & (heat > thr)
+    decisive = (gap.abs() > margin) & ((heat - thr).abs() > margin)
+    inb = torch.zeros_like(keep)
+    inb[:, border:H - border, border:W - border] = True
+    return keep & inb, decisive | ~inb
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_superpoint_fixture_is_self_consistent(name):
+    """The fixture's keypoints follow from its own dense heat map by the restated rule (this is what pins the test helper)."""
+    fx = _load(name)
+    batch, h, w, maxk, thr, _ = fx['case']
+    keep, _ = _decisions(fx['heat_f32'], 9, thr, 4, 0.0)
+    lafs, scores = fx['lafs'], fx['scores']
+    assert lafs.shape[0] == batch and lafs.shape[2:] == (2, 3)
+    assert torch.equal(lafs[..., :2], torch.eye(2).expand(batch, lafs.shape[1], 2, 2))
+    for b in range(batch):
+        xy = lafs[b, :, :, 2].long()
+        assert keep[b, xy[:, 1], xy[:, 0]].all()                          # every returned keypoint is a kept pixel
+        assert torch.equal(scores[b], fx['heat_f32'][b, xy[:, 1], xy[:, 0]])
+        n_kept = int(keep[b].sum())
+        assert lafs.shape[1] <= n_kept
+        if maxk != -1 and n_kept > maxk:
+            assert (scores[b][:-1] >= scores[b][1:]).all()                # top-k output is sorted
+    d = fx['descriptors']
+    assert (d.norm(dim=-1) - 1).abs().max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('name', CASES)
+def test_superpoint_matches_reference(name, precision):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    from gen_golden_superpoint import synthetic_superpoint_state_dict
+    from openglue_b200 import SuperPointNet
+    dev = torch.device('cuda:0')
+    fx = _load(name)
+    batch, h, w, maxk, thr, seed = fx['case']
+    model = SuperPointNet(max_keypoints=maxk, keypoint_threshold=thr, precision=precision)
+    model.load_state_dict(synthetic_superpoint_state_dict(seed), strict=True)           # the reference module's keys, strict
+    model = model.to(dev).eval()
+    lafs, scores, desc = model(fx['image'].to(dev))
+    # dense cell probabilities -> heat map, against the reference's fp64 layers
+    probs = model.last_probs
+    heat = probs[..., :64].reshape(batch, h // 8, w // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(batch, h, w).cpu()
+    err = float((heat.double() - fx['heat_f64'].double()).abs().max())
+    print(f'{name} {precision}: max |heat - ref64| {err:.2e}; keypoints {tuple(lafs.shape)}')
+    assert err <= 1e-5
+    # keypoints: identical wherever the reference's decision is decisive at 10x that error
+    lafs, scores, desc = lafs.cpu(), scores.cpu(), desc.cpu()
+    keep, decisive = _decisions(fx['heat_f64'].float(), 9, thr, 4, 10 * max(err, 1e-7))
+    assert torch.equal(lafs[..., :2], torch.eye(2).expand(batch, lafs.shape[1], 2, 2))
+    ref_lafs, ref_scores, ref_desc = fx['lafs'], fx['scores'], fx['descriptors']
+    all_decisive = bool(decisive.all())
+    if all_decisive:
+        assert lafs.shape == ref_lafs.shape
+    matched = 0
+    for b in range(batch):
+        ours = {(int(x), int(y)): j for j, (x, y) in enumerate(lafs[b, :, :, 2].tolist())}
+        for j, (x, y) in enumerate(ref_lafs[b, :, :, 2].long().tolist()):
+            if (x, y) in ours:
+                i = ours[(x, y)]
+                matched += 1
+                assert abs(float(scores[b, i]) - float(ref_scores[b, j])) <= 1e-5
+                assert (desc[b, i] - ref_desc[b, j]).abs().max() <= 1e-4
+            else:
+                assert not all_decisive, (b, x, y)
+    total = ref_lafs.shape[0] * ref_lafs.shape[1]
+    assert matched >= 0.99 * total, (matched, total)
+    if all_decisive and (maxk == -1 or name == 'superpoint_thr'):
+        pass
+    # ordering: where the reference's order is decided by score gaps larger than the error, ours is the same sequence
+    if all_decisive:
+        for b in range(batch):
+            gaps = (ref_scores[b][:-1] - ref_scores[b][1:]).abs()
+            if ref_lafs.shape[1] == lafs.shape[1] and (gaps > 10 * max(err, 1e-7)).all():
+                assert torch.equal(lafs[b, :, :, 2], ref_lafs[b, :, :, 2])
