@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .training import _Ops, _p
+from ._ops import _Ops, _p
 
 __all__ = ['SuperPointNet']
 
