@@ -22,7 +22,7 @@ import torch
 from . import _cabi
 from ._ops import _Ops, _p, _pad4  # noqa: F401  (tests build their torch double of the kernels on _Ops' composite helpers)
 
-__all__ = ['TrainStep', 'train_forward']
+__all__ = ['TrainStep', 'train_forward', 'GraphedTrainStep']
 
 
 class _BN:
@@ -359,3 +359,71 @@ def train_forward(model, data: dict) -> Dict[str, torch.Tensor]:
     names, params = zip(*[(n, p) for n, p in model.named_parameters()])
     scores, c0, c1 = _TrainFunction.apply(model, data, names, data['local_descriptors0'], data['local_descriptors1'], *params)
     return {'context_descriptors0': c0, 'context_descriptors1': c1, 'scores': scores}
+
+
+class GraphedTrainStep:
+    """The whole training step of one batch shape - train-mode forward, ``criterion``, backward, gradients into ``param.grad`` -
+    captured ONCE into a CUDA graph and replayed: the eager step issues ~5000 kernel launches from Python and is launch-rate-bound,
+    the replay costs the kernels' own time.  Labels (``generate_gt_matches``) and the optimiser stay outside::
+
+        step = GraphedTrainStep(model, data, y_true)          # model.train(); captures on the first batch
+        for data, y_true in loader:                           # same shapes
+            loss = step(data, y_true)                         # {'loss', 'metric_loss'}; gradients are in p.grad
+            optimizer.step()                                  # in-place updates keep the captured parameter addresses valid
+
+    The graph reads the parameters and BatchNorm buffers in place (so optimiser steps and running statistics carry over) and the
+    inputs from static copies.  Re-create the object when shapes change or parameters are re-allocated (``.to()``, ``load_state_dict``
+    keeps storage and is fine).  Results are bit-identical to the eager step (same kernels, same order)."""
+
+    _KEYS = ('keypoints0', 'keypoints1', 'side_info0', 'side_info1', 'local_descriptors0', 'local_descriptors1')
+
+    def __init__(self, model, data: dict, y_true: dict, nll_weight: float = 1.0):
+        from .losses import _run as criterion_run
+        if not model.training:
+            raise RuntimeError('GraphedTrainStep captures the training-mode step: call model.train() first')
+        dev = data['keypoints0'].device
+        if dev.type != 'cuda':
+            raise RuntimeError('openglue_b200 training needs CUDA tensors (sm_100a); there is no CPU path')
+        self.model, self.dev = model, dev
+        self.static = dict(data)
+        for k in self._KEYS:
+            self.static[k] = data[k].detach().float().contiguous().clone()
+        self.gt = {k: y_true[k].to(device=dev, dtype=torch.int64).contiguous().clone() for k in ('gt_matches0', 'gt_matches1')}
+        self.params = list(model.named_parameters())
+        for _, p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+
+        def run():
+            step = TrainStep(model, self.static)
+            scores, _, _ = step.forward()
+            loss, dscores = criterion_run(self.gt, {'scores': scores}, True, float(nll_weight))
+            grads = step.backward(dscores)
+            for name, p in self.params:
+                p.grad.copy_(grads[name].reshape(p.shape))
+            return loss, scores
+
+        with torch.cuda.device(dev):
+            saved = [b.clone() for b in model.buffers()]                # the warm-up run must not count as a training step
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                run()                                                    # builds function attributes, allocator pools
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for b, s in zip(model.buffers(), saved):
+                b.copy_(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.scores = run()
+
+    def __call__(self, data: dict, y_true: dict) -> Dict[str, torch.Tensor]:
+        for k in self._KEYS:
+            if tuple(data[k].shape) != tuple(self.static[k].shape):
+                raise ValueError(f'{k}: shape {tuple(data[k].shape)} differs from the captured {tuple(self.static[k].shape)}')
+            self.static[k].copy_(data[k], non_blocking=True)
+        for k in self.gt:
+            self.gt[k].copy_(y_true[k], non_blocking=True)
+        self.graph.replay()
+        return {'loss': self.loss[0], 'metric_loss': self.loss[1]}

@@ -51,3 +51,20 @@ p = [sum(x[i] for x in parts) / len(parts) for i in range(4)]
 print('train step: batch %d n %d m %d stages %d iters %d precision %s' % (batch, n, m, stages, iters, cfg['precision']))
 print('   labels %.2f ms | forward + loss %.2f ms | backward %.2f ms | Adam %.2f ms | total (device) %.2f ms | wall %.2f ms | %.1f pairs/s | loss %.4f'
       % (p[0], p[1], p[2], p[3], sum(p), wall, batch / (wall * 1e-3), float(l.detach())))
+
+# the same step captured once and replayed as one CUDA graph (openglue_b200.training.GraphedTrainStep)
+from openglue_b200.training import GraphedTrainStep
+data, y_true = generate_gt_matches(raw, f0, f1, 3.0, 5.0)
+g = GraphedTrainStep(model, data, y_true)
+for _ in range(2):
+    g(data, y_true); opt.step()
+torch.cuda.synchronize()
+e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+t0 = time.time()
+tg = ta = 0.0
+for _ in range(5):
+    e0.record(); l = g(data, y_true)['loss']; e1.record(); opt.step(); e2.record()
+    torch.cuda.synchronize(); tg += e0.elapsed_time(e1); ta += e1.elapsed_time(e2)
+wall = (time.time() - t0) / 5 * 1e3
+print('   as ONE CUDA graph: forward + loss + backward %.2f ms | Adam %.2f ms | wall %.2f ms | %.1f pairs/s | loss %.4f'
+      % (tg / 5, ta / 5, wall, batch / (wall * 1e-3), float(l)))

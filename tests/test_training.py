@@ -306,3 +306,39 @@ def test_training_step_pipeline_like_the_reference_module():
         opt.step()
         losses.append(float(total.detach()))
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.gpu
+def test_graphed_training_step_is_bit_identical_to_the_eager_step():
+    """GraphedTrainStep (the whole step replayed as one CUDA graph) against the eager autograd route: same loss, same gradients,
+    same BatchNorm buffers, bit for bit, over several optimiser steps."""
+    import copy
+    from openglue_b200 import SuperGlue, criterion
+    from openglue_b200.training import GraphedTrainStep
+    dev = torch.device('cuda:0')
+    fx = _load('train_ragged')
+    sd = synthetic_state_dict(fx['config'], seed=fx['weights_seed'])
+    sd.update(fx['bn_buffers'])
+    data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in fx['data'].items()}
+    y_true = {'gt_matches0': fx['gt_matches0'].to(dev), 'gt_matches1': fx['gt_matches1'].to(dev)}
+    models = []
+    for _ in range(2):
+        m = SuperGlue(dict(fx['config'], precision='tf32x3'))
+        m.load_state_dict(copy.deepcopy(sd), strict=True)
+        models.append(m.to(dev).train())
+    eager, graphed = models
+    opt_e = torch.optim.SGD(eager.parameters(), lr=1e-3)
+    opt_g = torch.optim.SGD(graphed.parameters(), lr=1e-3)
+    step = GraphedTrainStep(graphed, data, y_true)
+    for it in range(3):
+        opt_e.zero_grad()
+        loss_e = criterion(y_true, eager(data), margin=None)['loss']
+        loss_e.backward()
+        loss_g = step(data, y_true)['loss']
+        assert torch.equal(loss_e.detach(), loss_g), it
+        for (k, pe), (_, pg) in zip(eager.named_parameters(), graphed.named_parameters()):
+            assert torch.equal(pe.grad, pg.grad), (it, k)
+        opt_e.step()
+        opt_g.step()
+    for (k, be), (_, bg) in zip(eager.named_buffers(), graphed.named_buffers()):
+        assert torch.equal(be, bg), k
