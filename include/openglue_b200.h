@@ -357,6 +357,8 @@ int og_bn_train_bwd(const float* dy, int64_t lddy, const float* a, int64_t lda, 
 int og_softmax_rows(float* S, int64_t ld, int64_t rows, int cols, void* stream);
 int og_softmax_bwd_rows(const float* P, float* dP, int64_t ld, int64_t rows, int cols, float scale, void* stream);
 int og_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
+/* out[r, c] (+)= sum_s part[s][r, c] (s ascending; out row stride ld_out): reduction of the split-K weight gradients      */
+int og_sum_batches(const float* part, int S, int rows, int cols, float* out, int64_t ld_out, int accumulate, void* stream);
 int og_mix_fwd(const float* g, const float* l, const float* mix, float* out, int64_t rows, int d, void* stream);
 int og_mix_bwd(const float* dm, const float* mix, float* dg, float* dl, int64_t rows, int d, void* stream);
 int og_mix_param_grad(const float* colsum, const float* mix, float* dmix, int d, void* stream);

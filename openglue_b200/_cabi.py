@@ -101,6 +101,7 @@ SYMBOLS = {
     'og_softmax_rows': (_I, [_P, _L, _L, _I, _P]),
     'og_softmax_bwd_rows': (_I, [_P, _P, _L, _L, _I, _F, _P]),
     'og_axpby': (_I, [_P, _P, _F, _F, _P, _L, _P]),
+    'og_sum_batches': (_I, [_P, _I, _I, _I, _P, _L, _I, _P]),
     'og_mix_fwd': (_I, [_P, _P, _P, _P, _L, _I, _P]),
     'og_mix_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P]),
     'og_mix_param_grad': (_I, [_P, _P, _P, _I, _P]),

@@ -171,15 +171,42 @@ class _Ops:
                     'og_sinkhorn_bwd')
         return dZ, dd
 
+    def sum_batches(self, part, S, rows, cols, out, out_off, ld, accumulate=True):
+        _cabi.check(self.lib.og_sum_batches(_p(part), S, rows, cols, _p(out, out_off), ld, int(accumulate), self.st()), 'og_sum_batches')
+
+    def _transpose_chunks(self, X, S, Kc):
+        """[rows, cols] -> zero-padded [S, cols, Kc]: chunk s holds rows [s Kc, (s + 1) Kc) transposed"""
+        rows, cols = X.shape
+        out = self.zeros(S, cols, Kc) if rows != S * Kc else self.empty(S, cols, Kc)
+        nfull = rows // Kc
+        if nfull:
+            self.transpose_raw(X, 0, cols, Kc * cols, out, Kc, cols * Kc, nfull, Kc, cols, True)
+        if rows - nfull * Kc:
+            self.transpose_raw(X, nfull * Kc * cols, cols, 0, out[nfull], Kc, 0, 1, rows - nfull * Kc, cols, True)
+        return out
+
+    SPLIT_K = 512
+
     def grad_weight(self, dY, X, into, col_off=0):
-        """into[:, col_off : col_off + K] += dY^T X   (dY [rows, nout], X [rows, K], into [nout, ld])"""
+        """into[:, col_off : col_off + K] += dY^T X   (dY [rows, nout], X [rows, K], into [nout, ld]).  The contraction runs over the
+        rows (thousands) while the output is one or four GEMM tiles: it is split into chunks of SPLIT_K rows that run as ONE batched
+        GEMM (enough tiles for the whole GPU) and are summed in a fixed order."""
         rows, nout = dY.shape
         K = X.shape[1]
-        dYt = self.transpose(dY)                      # [1, nout, rp]
-        Xt = self.transpose(X)                        # [1, K, rp]
-        rp = dYt.shape[2]
         ld = into.stride(0)
-        self.gemm(dYt, rp, rp, Xt, rp, nout, K, into, ld, y_off=col_off, R=into, ldr=ld, r_off=col_off)
+        Kc = self.SPLIT_K
+        S = (rows + Kc - 1) // Kc
+        if S <= 1:
+            dYt = self.transpose(dY)                  # [1, nout, rp]
+            Xt = self.transpose(X)                    # [1, K, rp]
+            rp = dYt.shape[2]
+            self.gemm(dYt, rp, rp, Xt, rp, nout, K, into, ld, y_off=col_off, R=into, ldr=ld, r_off=col_off)
+            return
+        dYt = self._transpose_chunks(dY, S, Kc)       # [S, nout, Kc]
+        Xt = self._transpose_chunks(X, S, Kc)         # [S, K, Kc]
+        part = self.empty(S, nout, K)
+        self.gemm(dYt, Kc, Kc, Xt, Kc, nout, K, part, K, batch=S, strideA=nout * Kc, strideW=K * Kc, strideY=nout * K)
+        self.sum_batches(part, S, nout, K, into, col_off, ld, True)
 
     def grad_input(self, dY, W, k_off=0, k=None):
         """dY [rows, nout] . W[:, k_off : k_off + k] -> [rows, k]   (W [nout, ldw] row-major)"""

@@ -510,6 +510,14 @@ int og_softmax_bwd_rows(const float* P, float* dP, int64_t ld, int64_t rows, int
   return OG_OK;
 }
 
+int og_sum_batches(const float* part, int S, int rows, int cols, float* out, int64_t ld_out, int accumulate, void* stream) {
+  OG_CHECK_ARG(part && out && S > 0 && rows > 0 && cols > 0 && ld_out >= cols, "sum_batches: bad arguments");
+  sum_batches_kernel<<<eltwise_grid((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(part, S, rows, cols, out, ld_out, accumulate);
+  OG_LAUNCH_CHECK("sum_batches_kernel");
+  launch_counter()++;
+  return OG_OK;
+}
+
 int og_axpby(const float* x, const float* y, float a_, float b, float* out, int64_t n, void* stream) {
   OG_CHECK_ARG(x && out && n >= 0, "axpby: bad arguments");
   if (n == 0) return OG_OK;

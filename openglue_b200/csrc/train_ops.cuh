@@ -225,6 +225,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __re
   for (int j = lane; j < cols; j += 32) g[j] = scale * p[j] * (g[j] - dot);
 }
 
+// out[r * ld + c] (+)= sum_s part[s][r * cols + c], s ascending: the reduction behind the split-K weight gradients
+// (dW = sum over row chunks of dY_s^T X_s: one batched GEMM fills the GPU where a single [nout, K] output would occupy four CTAs)
+__global__ void __launch_bounds__(256) sum_batches_kernel(const float* __restrict__ part, int S, int rows, int cols, float* __restrict__ out,
+                                                          int64_t ld, int accumulate) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float t = 0.f;
+    for (int k = 0; k < S; ++k) t += part[(int64_t)k * n + i];
+    float* o = out + (i / cols) * ld + (i % cols);
+    *o = accumulate ? *o + t : t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // element-wise
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,

@@ -134,7 +134,8 @@ class _CpuOps:
 
     @staticmethod
     def _view(t, off, rows, cols, ld):
-        return torch.as_strided(t.detach().reshape(-1), (rows, cols), (ld, 1), off)
+        flat = t.detach().reshape(-1)                                     # (a view keeps its offset into the storage: as_strided's offset is absolute)
+        return torch.as_strided(flat, (rows, cols), (ld, 1), flat.storage_offset() + off)
 
     def gemm(self, A, lda, k1, W, ldw, rows, nout, Y, ldy, *, a_off=0, w_off=0, y_off=0, A2=None, lda2=0, k2=0, a2_off=0, bias=None,
              relu=False, alpha=1.0, R=None, ldr=0, r_off=0, batch=1, strideA=0, strideA2=0, strideW=0, strideY=0, strideR=0,
@@ -235,9 +236,15 @@ class _CpuOps:
             return out
         return r
 
+    def sum_batches(self, part, S, rows, cols, out, out_off, ld, accumulate=True):
+        t = part.reshape(S, rows, cols).sum(0)
+        dst = self._view(out, out_off, rows, cols, ld)
+        dst.copy_(dst + t if accumulate else t)
+
     # composite helpers: the product's own code, running on this double
     from openglue_b200.training import _Ops as _P
     linear, transpose, grad_weight, grad_input = _P.linear, _P.transpose, _P.grad_weight, _P.grad_input
+    _transpose_chunks, SPLIT_K = _P._transpose_chunks, 32              # (small chunks: the fixtures have ~100-400 rows per image)
 
 
 @pytest.mark.parametrize('name', TRAIN_CASES)
