@@ -104,8 +104,19 @@ class _Ops:
         return out
 
     def attention(self, q, k, v, B, nq, nk, H, dh):
+        """fused softmax attention (forward): the tcgen05 3xTF32 kernel for head_dim 32 / 64 (K and V^T as tf32 hi/lo operands),
+        the fp32 CUDA-core kernel otherwise / in fp32 mode"""
         d = H * dh
         o = self.empty(B * nq, d)
+        if self.prec != _cabi.OG_PREC_FP32 and dh in (32, 64):
+            khi, klo = torch.empty_like(k), torch.empty_like(k)
+            _cabi.check(self.lib.og_split_tf32(_p(k), _p(khi), _p(klo), k.numel(), self.st()), 'og_split_tf32')
+            vt = self.transpose(v, batch=B, rows=nk, cols=d)            # [B, d, pad4(nk)], zero padded
+            vthi, vtlo = torch.empty_like(vt), torch.empty_like(vt)
+            _cabi.check(self.lib.og_split_tf32(_p(vt), _p(vthi), _p(vtlo), vt.numel(), self.st()), 'og_split_tf32')
+            _cabi.check(self.lib.og_attention_tc_fwd(_p(q), d, nq * d, _p(khi), _p(klo), d, _p(vthi), _p(vtlo), vt.shape[2], _p(o), d, nq * d,
+                                                     B, nq, nk, H, dh, self.st()), 'og_attention_tc_fwd')
+            return o
         _cabi.check(self.lib.og_attention_fwd(_p(q), d, nq * d, _p(k), d, nk * d, _p(v), d, nk * d, _p(o), d, nq * d, B, nq, nk, H, dh,
                                               _cabi.OG_PREC_FP32, self.st()), 'og_attention_fwd')
         return o
