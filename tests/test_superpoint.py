@@ -102,3 +102,38 @@ def test_superpoint_matches_reference(name, precision):
             gaps = (ref_scores[b][:-1] - ref_scores[b][1:]).abs()
             if ref_lafs.shape[1] == lafs.shape[1] and (gaps > 10 * max(err, 1e-7)).all():
                 assert torch.equal(lafs[b, :, :, 2], ref_lafs[b, :, :, 2])
+
+
+@pytest.mark.gpu
+def test_image_pair_to_matches_pipeline():
+    """Front-end -> matching core, device-resident: SuperPointNet on two views of one synthetic scene (the second a shifted crop),
+    keypoints / scores / descriptors handed to MatchingCore as inference.py does (keypoints = lafs[..., 2], side info = the detector
+    response), mutual matches out.  Random weights: the check is plumbing (shapes, finiteness, index ranges, mutual consistency)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    from gen_golden_superpoint import synthetic_superpoint_state_dict, synthetic_images
+    from openglue_b200 import MatchingCore, SuperGlue, SuperPointNet
+    from openglue_b200.synthetic import default_config, synthetic_state_dict
+    dev = torch.device('cuda:0')
+    sp = SuperPointNet(max_keypoints=256)
+    sp.load_state_dict(synthetic_superpoint_state_dict(7), strict=True)
+    sp = sp.to(dev).eval()
+    scene = synthetic_images(2, 256, 320, 9).to(dev)
+    img0, img1 = scene[:, :, :240, :304].contiguous(), scene[:, :, 16:, 16:].contiguous()       # two 240 x 304 views, shifted by (16, 16)
+    lafs0, sc0, d0 = sp(img0)
+    lafs1, sc1, d1 = sp(img1)
+    assert lafs0.shape[1] == 256 and lafs1.shape[1] == 256 and d0.shape == (2, 256, 256)
+    cfg = default_config(descriptor_dim=256, num_stages=2, num_iters=20)
+    sg = SuperGlue(cfg)
+    sg.load_state_dict(synthetic_state_dict(cfg, seed=3), strict=True)
+    core = MatchingCore(sg.to(dev).eval(), 0.0)
+    data = {'keypoints0': lafs0[:, :, :, 2].contiguous(), 'keypoints1': lafs1[:, :, :, 2].contiguous(),
+            'side_info0': sc0[..., None].contiguous(), 'side_info1': sc1[..., None].contiguous(),
+            'local_descriptors0': d0, 'local_descriptors1': d1, 'image0_size': (304, 240), 'image1_size': (304, 240)}
+    out = core(data, want_scores=True)
+    m0, m1 = out['matches0'].cpu(), out['matches1'].cpu()
+    assert torch.isfinite(out['scores']).all()
+    assert m0.shape == (2, 256) and int(m0.max()) < 256 and int(m0.min()) >= -1
+    for b in range(2):                                                   # mutual: matches1[matches0[i]] == i
+        i = (m0[b] >= 0).nonzero()[:, 0]
+        assert torch.equal(m1[b, m0[b, i]], i)
