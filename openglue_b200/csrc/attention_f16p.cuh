@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(tcap::THREADS, 1) attention_f16p_kernel(const 
 
   launch_dependents();
   extern __shared__ uint8_t og_tcap_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcap_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tcap_smem_raw);
   uint8_t* sK = smem;
   uint8_t* sV = smem + STAGES * k_stage_bytes<CG>();
   Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<CG>());

@@ -21,6 +21,27 @@
 #include <stdlib.h>
 #include <algorithm>
 
+// OG_ATTN_EARLY_S (default 0 until verified on the GPU): the QK^T issuer waits for "S_{i-2} is in the team's registers" (s_free, arrived right after the
+// tcgen05.ld of the logits) instead of "P_{i-2} has been written" (p_full, ~1300 cycles later).  The event trace of the p_full form
+// (profiles/r02_trace_attention_f16_two_teams.txt) shows QK^T_{i+2} issued the moment P_i is handed over and its logits seen ~830
+// cycles after that: a team's cycle was softmax (1650) + MMA round trip (830) per two key blocks.  S and P occupy disjoint TMEM
+// columns, so the next QK^T of a buffer only has to wait for the load.
+#ifndef OG_ATTN_EARLY_S
+#define OG_ATTN_EARLY_S 0
+#endif
+// OG_ATTN_FOLD_EARLY (default 0, experiment): fold O_{i-2} into the registers BEFORE the exponentials of block i (in four
+// 8-column loads: the logits are live) instead of after P_i has been handed over, so that P.V_i never waits for the fold.
+#ifndef OG_ATTN_FOLD_EARLY
+#define OG_ATTN_FOLD_EARLY 0
+#endif
+// OG_ATTN_MERGER_LAST (default 0, experiment): the team that owns a tile's LAST key block merges and stores the tile; the other
+// team deposits its partial result (bar.arrive, no wait) and starts the next tile's first block, which is the earlier one.
+// With the merge fixed on team 0 and an even block count, team 0 waited half a cycle for team 1's last block, merged (~2500
+// cycles) and only then turned to a block whose logits had been ready all along (~6000 cycles per tile boundary in the trace).
+#ifndef OG_ATTN_MERGER_LAST
+#define OG_ATTN_MERGER_LAST 0
+#endif
+
 namespace og {
 namespace tcat {
 constexpr int BM = 128, BNK = 64, DH = 64, HD = 32;
@@ -36,7 +57,7 @@ constexpr int REGS_SOFTMAX = 104, REGS_PRODUCER = 64;        // setmaxnreg moves
 
 struct __align__(16) Barriers {
   uint64_t k_full[MAX_STAGES], k_empty[MAX_STAGES], v_full[MAX_STAGES], v_empty[MAX_STAGES];
-  uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2];
+  uint64_t q_ready, q_free, s_full[2], p_full[2], o_full[2], o_empty[2], s_free[2];
   uint32_t tmem_base;
 };
 template <int CG> __host__ __device__ constexpr int k_stage_bytes() { return 2 * (BNK / CG) * 128; }
@@ -79,7 +100,7 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
 
   launch_dependents();
   extern __shared__ uint8_t og_tcat_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcat_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tcat_smem_raw);
   uint8_t* sK = smem;
   uint8_t* sV = smem + STAGES * k_stage_bytes<CG>();
   Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<CG>());
@@ -114,6 +135,7 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
     for (int j = 0; j < 2; ++j) {                    // buffer j belongs to team j: eight warps per CTA
       mbar_init(&bars->s_full[j], 1); mbar_init(&bars->p_full[j], 8 * CG);
       mbar_init(&bars->o_full[j], 1); mbar_init(&bars->o_empty[j], 8 * CG);
+      mbar_init(&bars->s_free[j], 8 * CG);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_khi); prefetch_tensormap(&map_klo);
@@ -186,7 +208,11 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
         const int s = i % STAGES, ph = (i / STAGES) & 1, j = i & 1;
         OG_TRACE_EVT(0, i);
         mbar_wait_t(&bars->k_full[s], ph);
+#if OG_ATTN_EARLY_S
+        if (i >= 2) mbar_wait_t(&bars->s_free[j], ((i - 2) >> 1) & 1);     // team j holds S_{i-2} in registers (S and P columns are disjoint)
+#else
         if (i >= 2) mbar_wait_t(&bars->p_full[j], ((i - 2) >> 1) & 1);     // team j has read S_{i-2} out of its buffer
+#endif
         tc_fence_after();
         OG_TRACE_EVT(1, i);
         if (elect_one()) {
@@ -340,6 +366,10 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       uint32_t s[32];
       tmem_ld_32x32(sp + 32 * g, s);
       tmem_wait_ld();
+#if OG_ATTN_EARLY_S
+      tc_fence_before();
+      arrive_leader(&bars->s_free[team]);            // QK^T_{i+2} may overwrite the S columns from here on
+#endif
       if (kbase + 32 > a.nk) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) if (kbase + c >= a.nk) s[c] = __float_as_uint(-CUDART_INF_F);
@@ -356,10 +386,29 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       const float corr = ex2_approx(mc_run - mc);
       const unsigned long long nmc2 = pack2(-mc, -mc);
       unsigned long long rs2 = 0ull;
+#if OG_ATTN_FOLD_EARLY
+      if (prev >= 0) {                                 // P_i goes where P_prev sits: the team's previous P.V must have read it;
+        mbar_wait_t(bar_of, (prev >> 1) & 1);            // its result is folded right here, 8 columns at a time
+        tc_fence_after();
+        const unsigned long long corr2 = pack2(corr_prev, corr_prev);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[8];
+          tmem_ld_32x8(o_addr + 8 * q, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            acc2[4 * q + c] = ffma2(acc2[4 * q + c], corr2, pack2(__uint_as_float(o[2 * c]), __uint_as_float(o[2 * c + 1])));
+        }
+        tc_fence_before();
+        arrive_leader(bar_oe);
+      }
+#else
       if (prev >= 0) {                                 // P_i goes where P_prev sits: the team's previous P.V must have read it
         mbar_wait_t(bar_of, (prev >> 1) & 1);            // (issued a block and a half ago: no wait in steady state; folded below)
         tc_fence_after();
       }
+#endif
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {                 // two halves of 16 columns: P leaves the registers as soon as it is split
         uint32_t hi[8], lo[8];
@@ -390,24 +439,40 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       unpack2(rs2, r0, r1);
       l_run = fmaf(l_run, corr, r0 + r1);
       m_run = m_new; mc_run = mc;
+#if !OG_ATTN_FOLD_EARLY
       if (prev >= 0) fold_o(prev, corr_prev);
+#endif
       prev = i; corr_prev = corr;
     }
     if (prev >= 0) fold_o(prev, corr_prev);
 
-    // ---- merge the two teams' partial results of this tile (team 1 -> shared memory -> team 0), normalise, store
+    // ---- merge the two teams' partial results of this tile (depositor -> shared memory -> merger), normalise, store
     const int tp2 = nt & 1;
+#if OG_ATTN_MERGER_LAST
+    const int merger = (it0 + nblk - 1) & 1;          // the team that finishes the tile LAST merges; the other one deposits and moves on
+#else
+    const int merger = 0;
+#endif
     float* lm_t = lm + tp2 * (2 * 2 * 128 * 2);
     reinterpret_cast<float2*>(lm_t)[(team * 2 + g) * 128 + trow] = make_float2(mc_run, l_run);
-    if (team == 1) {
+    if (team != merger) {
       float* mr = mrg + ((tp2 * 2 + g) * 128 + trow) * MRG_STRIDE;
 #pragma unroll
       for (int c = 0; c < 16; ++c) { float x, y; unpack2(acc2[c], x, y); mr[2 * c] = x; mr[2 * c + 1] = y; }
     }
+#if OG_ATTN_MERGER_LAST
+    if (team != merger) {                            // producer side of the named barrier: no wait (PTX bar.arrive / bar.sync pattern)
+      __threadfence_block();
+      asm volatile("bar.arrive 3, 512;" ::: "memory");
+    } else {
+      asm volatile("bar.sync 3, 512;" ::: "memory");
+    }
+#else
     asm volatile("bar.sync 3, 512;" ::: "memory");
-    if (team == 0) {
+#endif
+    if (team == merger) {
       const float2* lmv = reinterpret_cast<const float2*>(lm_t);
-      const float2 a0 = lmv[(0 * 2 + (g ^ 1)) * 128 + trow], b0 = lmv[(1 * 2 + 0) * 128 + trow], b1 = lmv[(1 * 2 + 1) * 128 + trow];
+      const float2 a0 = lmv[(team * 2 + (g ^ 1)) * 128 + trow], b0 = lmv[((team ^ 1) * 2 + 0) * 128 + trow], b1 = lmv[((team ^ 1) * 2 + 1) * 128 + trow];
       const float mc0 = mc_run, mc1 = b0.x;            // the two warpgroups of a team share their running maximum
       const float mcf = fmaxf(mc0, mc1);
       const float f0 = ex2_approx(mc0 - mcf), f1 = ex2_approx(mc1 - mcf);     // a team without blocks: 2^(-inf) = 0
@@ -441,7 +506,7 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
       __syncwarp();
     }
     }
-    if (sc.out_amax && team == 0) {
+    if (sc.out_amax) {                               // both teams may have merged tiles
       omax = warp_max(omax);
       if (lane == 0 && omax > 0.f) atomic_amax(sc.out_amax, omax);
     }

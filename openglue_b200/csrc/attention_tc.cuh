@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(tca::THREADS, 1) attention_tc_kernel(const __g
 
   launch_dependents();                                       // the next kernel may take this SM as soon as this CTA leaves it
   extern __shared__ uint8_t og_tca_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tca_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tca_smem_raw);
   uint8_t* sK = smem;
   uint8_t* sV = smem + STAGES * k_stage_bytes<DH, CG>();
   Barriers* bars = reinterpret_cast<Barriers*>(sV + STAGES * v_stage_bytes<DH, CG>());

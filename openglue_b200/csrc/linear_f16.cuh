@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
   constexpr bool r_tma = RTMA != 0;
   launch_dependents();
   extern __shared__ uint8_t og_tcf_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcf_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tcf_smem_raw);
   uint8_t* sm_a = smem;                                                  // [AST][32 KB] raw fp32 A tiles
   uint8_t* sm_b = smem + AST * A_BYTES;                                  // [BST][B_hi | B_lo]
   uint8_t* s_out = sm_b + BST * B_STAGE;                                  // [2 warpgroups][2 buffers][16 KB]

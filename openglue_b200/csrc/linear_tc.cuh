@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(tcl::THREADS) linear_tc_kernel(const __grid_co
   using namespace tcl;
   using namespace tc;
   extern __shared__ uint8_t og_tcl_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tcl_smem_raw);
   uint8_t* sB = smem;                                                     // [B_STAGES][hi|lo][16 KB]
   uint8_t* sA = smem + B_STAGES * 2 * TILE_BYTES;                         // MODE_SS only
   Barriers* bars = reinterpret_cast<Barriers*>(smem + B_STAGES * 2 * TILE_BYTES + (MODE == MODE_SS ? A_STAGES * 2 * TILE_BYTES : 0));

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(tcl2::THREADS, 1) linear_tc2_kernel(const __gr
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_TILE = C::B_TILE, NC = PAIR ? 2 : 1;
   launch_dependents();                                       // the next kernel may take this SM as soon as this CTA leaves it
   extern __shared__ uint8_t og_tcl2_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(og_tcl2_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tc::align_smem_1024(og_tcl2_smem_raw);
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;                          // [2 warpgroups][2 buffers][16 KB]
   Barriers* bars = reinterpret_cast<Barriers*>(s_out + OUT_BYTES);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform by construction

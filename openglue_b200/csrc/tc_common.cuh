@@ -15,6 +15,14 @@ namespace tc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 1024-byte alignment of the dynamic shared-memory block (128-byte swizzled TMA tiles), computed as an OFFSET from the
+// __shared__ symbol: rounding the pointer up through uintptr_t hides the address space from the compiler and every
+// shared-memory access of the kernel becomes a generic LD.E / ST.E with 64-bit address arithmetic (61 + 58 of them in the
+// fp16 attention kernel, on the softmax chain's critical path) instead of LDS / STS.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  const uint32_t b = smem_u32(raw);
+  return raw + (((b + 1023u) & ~1023u) - b);
+}
 
 // ----------------------------------------------------------------------------- single-lane election
 // elect.sync tells ptxas that exactly one lane runs the guarded region, so operands of the uniform-datapath
@@ -201,6 +209,12 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
