@@ -13,7 +13,8 @@ NCCL all-reduce of the per-rank match statistics per step mirrors the reference'
 
 Prints ONE JSON line (rank 0).  Keys follow the driver's contract; `roofline` is measured live
 on the dominant kernel through the operator-level C-ABI call, `cpu_baseline` / `--impl reference`
-time the oracle port (same ATen ops as the reference's PyTorch-CPU path) on the host cores.
+time the unmodified reference module staged under oracle/_ref (oracle/build_ref.py; `kind: "reference"`) on the host
+cores, or - when it is not staged - the oracle port (same ATen ops, bit-identical outputs; `kind: "port"`).
 """
 from __future__ import annotations
 
@@ -148,16 +149,35 @@ def _numa_nodes():
     return nodes or [allowed]
 
 
+def _reference_kind():
+    """'reference' when the unmodified reference is staged under oracle/_ref (oracle/build_ref.py; it travels to the GPU box),
+    else 'port' (the oracle restatement: the same ATen calls, bit-identical outputs - tests/test_oracle_golden.py)."""
+    from oracle.build_ref import available
+    return 'reference' if available() else 'port'
+
+
 def _oracle_times(cfg, n, m, reps, threads, family='planted'):
     from oracle import superglue_oracle as O                  # checker / CPU baseline only
+    from oracle.build_ref import import_reference
     sd = synthetic_state_dict(cfg, seed=0)
     data = synthetic_pairs(1, n, m, cfg['descriptor_dim'], cfg['positional_encoding']['side_info_size'], family=family, seed=1234)
     torch.set_num_threads(threads)
-    O.run(sd, cfg, data, MATCH_THRESHOLD)                     # warm-up at this thread count
+    ref = import_reference()
+    if ref is not None:                                       # the reference's own module + the match extraction of matching_module.py:175-181
+        model = ref[0](dict(cfg)).eval()
+        model.load_state_dict(sd)
+
+        def run():
+            with torch.no_grad():
+                return O.extract_matches(model(data)['scores'], MATCH_THRESHOLD)
+    else:
+        def run():
+            return O.run(sd, cfg, data, MATCH_THRESHOLD)
+    run()                                                     # warm-up at this thread count
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        O.run(sd, cfg, data, MATCH_THRESHOLD)
+        run()
         times.append(time.perf_counter() - t0)
     return times
 
@@ -221,8 +241,8 @@ def time_oracle(workload, cfg, n, m, reps):
 
 
 def run_reference(args, wl):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores
-    (oracle port; /root/reference is Python and does not travel to the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores: the unmodified reference module
+    staged under oracle/_ref by oracle/build_ref.py (kind "reference"), else the oracle port (kind "port")."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -231,7 +251,9 @@ def run_reference(args, wl):
     r = time_oracle(args.workload, cfg, wl['n'], wl['m'], max(1, args.steps))
     value = max(r['single'], r.get('aggregate', 0.0))         # all the host threads it can use
     cores = r['procs'] * r['cores_per_proc'] if r.get('aggregate', 0.0) >= r['single'] else r['threads']
-    sample = (f'1 pair per step of the {args.workload} shape (N={wl["n"]}, M={wl["m"]}), torch CPU fp32 (oracle port = the reference\'s ATen ops); '
+    kind = _reference_kind()
+    what = 'the unmodified reference SuperGlue module from oracle/_ref + its match extraction' if kind == 'reference' else 'oracle port = the reference\'s ATen ops'
+    sample = (f'1 pair per step of the {args.workload} shape (N={wl["n"]}, M={wl["m"]}), torch CPU fp32 ({what}); '
               f'single process pinned to NUMA node 0 ({r["node0_cpus"]} cpus), {r["threads"]} threads (best of a sweep): {r["single"]:.3f} pairs/s; '
               f'{r["procs"]} processes side by side x {r["cores_per_proc"]} pinned cores: {r.get("aggregate", 0.0):.3f} pairs/s aggregate; '
               f'value = the larger; host: {r["cpus"]} cpus, {r["numa_nodes"]} NUMA nodes')
@@ -240,7 +262,7 @@ def run_reference(args, wl):
         'steps': args.steps, 'warmup': 1, 'ms_per_step': 1e3 / value, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': bench_config(args, wl, per_gpu_batch=1),
-        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': kind, 'sample': sample,
                          'single_process': r['single'], 'aggregate': r.get('aggregate')},
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -526,9 +548,9 @@ def main():
         r = time_oracle(args.workload, default_config(**wl['cfg']), n, m, 3)
         agg = r.get('aggregate', 0.0)
         line['cpu_baseline'] = {'value': max(r['single'], agg), 'unit': 'pairs/s',
-                                'cores': r['procs'] * r['cores_per_proc'] if agg >= r['single'] else r['threads'], 'kind': 'port',
+                                'cores': r['procs'] * r['cores_per_proc'] if agg >= r['single'] else r['threads'], 'kind': _reference_kind(),
                                 'single_process': r['single'], 'aggregate': agg,
-                                'sample': f'single pairs of the {args.workload} shape (N={n}, M={m}), torch CPU fp32 (oracle port); one process '
+                                'sample': f'single pairs of the {args.workload} shape (N={n}, M={m}), torch CPU fp32 ({"unmodified reference module, oracle/_ref" if _reference_kind() == "reference" else "oracle port"}); one process '
                                           f'pinned to NUMA node 0 ({r["node0_cpus"]} cpus, {r["threads"]} threads, best of 3 after warm-up): '
                                           f'{r["single"]:.3f} pairs/s; {r["procs"]} processes x {r["cores_per_proc"]} pinned cores side by side: '
                                           f'{agg:.3f} pairs/s aggregate; value = the larger; host: {r["cpus"]} cpus, {r["numa_nodes"]} NUMA nodes'}

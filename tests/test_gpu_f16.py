@@ -166,6 +166,43 @@ def test_attention_f16_operator(B, H, nq, nk, pair):
     assert float(oamax) == float(out.abs().max())
 
 
+@pytest.mark.parametrize('B,H,nq,nk,pair', [
+    (10, 4, 1024, 1216, 1),      # 160 tiles on 74 CTA pairs: several tiles per pair, 19 key blocks (odd: the teams swap roles every tile)
+    (12, 4, 1000, 1100, 1),      # 192 tiles, 18 key blocks (even), ragged rows and keys
+    (6, 4, 700, 64, 1),          # one key block per tile: one team has no block at all
+    (5, 4, 1024, 1216, 0)])      # single-CTA form, several tiles per CTA
+def test_attention_f16_many_tiles(B, H, nq, nk, pair):
+    """The persistent loop of the fp16 attention kernel: tile hand-over (next Q, merge of the two teams' partial results, barrier
+    phases across tiles).  Reference: plain torch float64 on the device (the same arithmetic as oracle.softmax_attention)."""
+    dh = 64
+    g = torch.Generator(device=DEV).manual_seed(2)
+    d = H * dh
+    q, k, v = (3 * torch.randn(B, n_, d, generator=g, device=DEV) for n_ in (nq, nk, nk))
+    hv = lambda t, n: t.double().reshape(B, n, H, dh).permute(0, 2, 1, 3)
+    ref = (torch.softmax(hv(q, nq) @ hv(k, nk).transpose(2, 3) / dh ** 0.5, dim=-1) @ hv(v, nk)).permute(0, 2, 1, 3).reshape(B, nq, d)
+    kh, kl, kmeta = split16(k.reshape(B * nk, d))
+    ldvt = (nk + 7) // 8 * 8
+    vt = torch.zeros(B * d, ldvt, device=DEV)
+    vt[:, :nk] = v.transpose(1, 2).reshape(B * d, nk)
+    vth, vtl, vmeta = split16(vt)
+    out = torch.full((B, nq, d), float('nan'), device=DEV)
+    oamax = torch.zeros(1, device=DEV)
+    lib = _cabi.lib()
+    lib.og_set_tuning(-1, pair)
+    try:
+        for _ in range(2):                           # the second launch reuses nothing: barriers and TMEM are per launch
+            rc = lib.og_attention_f16_fwd(_p(q), d, nq * d, _p(amax_of(q)), _p(kh), _p(kl), d, _p(kmeta), _p(vth), _p(vtl), ldvt, _p(vmeta),
+                                          _p(out), d, nq * d, _p(oamax), B, nq, nk, H, dh, 0, _st())
+            _cabi.check(rc, 'og_attention_f16_fwd')
+        torch.cuda.synchronize()
+    finally:
+        lib.og_set_tuning(-1, 1)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f'\n[attention_f16 many tiles B{B} H{H} {nq}x{nk} pair={pair}] rel err {err:.2e}')
+    assert err <= 5e-6
+    assert float(oamax) == float(out.abs().max())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('batch,n,m', [(2, 330, 197), (1, 256, 256), (3, 64, 1)])
 def test_fused_projections_are_bit_identical(batch, n, m):
