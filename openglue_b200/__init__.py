@@ -10,13 +10,13 @@ and the steps either side of those:
     criterion(y_true, y_pred, margin=None) -> {'loss', 'metric_loss'}
     matching_log_probs(S, dustbin_score, num_iters, reg)      (differentiable Sinkhorn: forward + backward kernels)
     SuperGlue(config).train()(data)                           (training mode: batch-statistics BatchNorm, explicit backward pass)
-    SuperPointNet(max_keypoints, ...)(image) -> (lafs, scores, descriptors)   (the detector / descriptor front-end)
+    SuperPointNet(max_keypoints, ...)(image) -> (lafs, scores, descriptors)   (the detector / descriptor front-end; SuperPointNetBn: its BatchNorm variant)
 """
 from .gt_matches import generate_gt_matches  # noqa: F401
 from .feature_cache import FeatureStore, collate_features  # noqa: F401
 from .losses import criterion  # noqa: F401
 from .sinkhorn import matching_log_probs  # noqa: F401
 from .superglue import MatchingCore, PendingMatches, SuperGlue  # noqa: F401
-from .superpoint import SuperPointNet  # noqa: F401
+from .superpoint import SuperPointNet, SuperPointNetBn  # noqa: F401
 
 __version__ = '0.1.0'

@@ -8,7 +8,9 @@ convolution is an im2col gather + one GEMM with bias / ReLU fused (3xTF32 tcgen0
 run the exact fp32 kernel), then max-pool, channel norm, cell softmax, pixel heat map + non-maximum suppression + threshold + border
 removal, ordered compaction, top-k and bilinear descriptor sampling as one kernel each.  The only host step is reading the
 per-image keypoint counts (the reference's ``torch.nonzero`` synchronises in the same place) to size the output.
-``SuperPointNetBn`` (BatchNorm variant, model.py:132-175) is not built.  There is no CPU path.
+``SuperPointNetBn`` (BatchNorm variant, model.py:132-199: conv -> BatchNorm2d -> ReLU, also behind the two 1x1 heads) is the
+same kernel schedule on folded weights: in eval mode ``BN(W x + b) = (g / sqrt(var + eps)) W x + (b - mean) g / sqrt(var + eps) + beta``,
+folded once in float64 on the host.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ import torch.nn as nn
 from . import _cabi
 from ._ops import _Ops, _p
 
-__all__ = ['SuperPointNet']
+__all__ = ['SuperPointNet', 'SuperPointNetBn']
 
 _MAX_CAND = 16384
 
@@ -48,14 +50,19 @@ class SuperPointNet(nn.Module):
             print(self.load_state_dict(torch.load(str(weights), map_location='cpu'), strict=True))
 
     # ------------------------------------------------------------------ weights: [Cout, Cin, 3, 3] -> [Cout, (3 ky + kx) Cin + ci]
+    def _conv_params(self, name, m):
+        """(weight [Cout, Cin, kh, kw], bias [Cout]) the kernels run for convolution `name` (hook: SuperPointNetBn folds its BatchNorm in)"""
+        return m.weight.detach(), m.bias.detach()
+
     def _weights(self):
-        key = tuple((p._version, p.data_ptr()) for p in self.parameters())
+        key = tuple((p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
         if self._packed is None or self._packed[0] != key:
             w = {}
             for name, m in self.named_children():
                 if isinstance(m, nn.Conv2d):
-                    co, ci, kh, kw = m.weight.shape
-                    w[name] = (m.weight.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous(), m.bias.detach().contiguous())
+                    wt, bias = self._conv_params(name, m)
+                    co, ci, kh, kw = wt.shape
+                    w[name] = (wt.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous(), bias.contiguous())
             self._packed = (key, w)
         return self._packed[1]
 
@@ -142,3 +149,44 @@ class SuperPointNet(nn.Module):
             lafs[:, :, 1, 1] = 1.0
             lafs[:, :, :, 2] = kpts
         return lafs, scores, desc
+
+
+class SuperPointNetBn(SuperPointNet):
+    """Drop-in for the reference's ``SuperPointNetBn`` (models/features/superpoint/model.py:132-199): every convolution is followed by
+    a BatchNorm2d (``bn1a`` ... ``bn4b``, ``bnPa``, ``bnPb``, ``bnDa``, ``bnDb``; same ``state_dict`` keys, same checkpoint format
+    ``{'model_state_dict': ...}`` with the U-Net style key names renamed by ``rename_weights_keys``).  Inference only: the
+    normalisation uses the running statistics and is folded into the convolution it follows, so the forward pass is
+    ``SuperPointNet``'s kernel schedule, unchanged."""
+
+    def __init__(self, max_keypoints: int = -1, descriptor_dim: int = 256, nms_kernel: int = 9, remove_borders_size: int = 4,
+                 keypoint_threshold: float = 0.0, weights: Optional[Union[str, pathlib.Path]] = None, precision: str = 'tf32x3'):
+        super().__init__(max_keypoints, descriptor_dim, nms_kernel, remove_borders_size, keypoint_threshold, weights=None, precision=precision)
+        for i, ch in enumerate(self.layers_channels):                       # model.py:141-148
+            setattr(self, f'bn{i + 1}a', nn.BatchNorm2d(ch[1]))
+            setattr(self, f'bn{i + 1}b', nn.BatchNorm2d(ch[3]))
+        self.bnPa, self.bnPb = nn.BatchNorm2d(256), nn.BatchNorm2d(65)
+        self.bnDa, self.bnDb = nn.BatchNorm2d(256), nn.BatchNorm2d(256)
+        if weights is not None:                                             # model.py:173-178
+            sd = self.rename_weights_keys(torch.load(str(weights), map_location='cpu')['model_state_dict'])
+            print(self.load_state_dict(sd, strict=True))
+
+    _RENAMES = [('inc.conv.conv.0', 'conv1a'), ('inc.conv.conv.1', 'bn1a'), ('inc.conv.conv.3', 'conv1b'), ('inc.conv.conv.4', 'bn1b')] + [
+        (f'down{i}.mpconv.1.conv.{j}', f'{kind}{i + 1}{ab}') for i in (1, 2, 3)
+        for j, kind, ab in ((0, 'conv', 'a'), (1, 'bn', 'a'), (3, 'conv', 'b'), (4, 'bn', 'b'))]
+
+    @staticmethod
+    def rename_weights_keys(state_dict):
+        """checkpoint key names of the BatchNorm SuperPoint release -> this module's (model.py:151-171)"""
+        for key in list(state_dict.keys()):
+            new = key
+            for old, repl in SuperPointNetBn._RENAMES:
+                new = new.replace(old, repl)
+            state_dict[new] = state_dict.pop(key)
+        return state_dict
+
+    def _conv_params(self, name, m):
+        bn = getattr(self, 'bn' + name[4:])                                 # conv1a -> bn1a, convPb -> bnPb
+        g = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        wt = m.weight.detach().double() * g.view(-1, 1, 1, 1)
+        bias = (m.bias.detach().double() - bn.running_mean.detach().double()) * g + bn.bias.detach().double()
+        return wt.float(), bias.float()

@@ -58,6 +58,21 @@ def synthetic_superpoint_state_dict(seed: int, descriptor_dim: int = 256):
     return sd
 
 
+def synthetic_superpoint_bn_state_dict(seed: int):
+    """SuperPointNetBn (model.py:132-199): the convolutions of `synthetic_superpoint_state_dict` + BatchNorm2d parameters and running
+    statistics that are far from the identity (scale 0.5 .. 1.5, shifts, variances 0.3 .. 2), so that a wrong fold cannot pass."""
+    sd = synthetic_superpoint_state_dict(seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    for name, ch in [('bn1a', 64), ('bn1b', 64), ('bn2a', 64), ('bn2b', 64), ('bn3a', 128), ('bn3b', 128), ('bn4a', 128), ('bn4b', 128),
+                     ('bnPa', 256), ('bnPb', 65), ('bnDa', 256), ('bnDb', 256)]:
+        sd[name + '.weight'] = 0.5 + torch.rand(ch, generator=g)
+        sd[name + '.bias'] = 0.2 * torch.randn(ch, generator=g)
+        sd[name + '.running_mean'] = 0.3 * torch.randn(ch, generator=g)
+        sd[name + '.running_var'] = 0.3 + 1.7 * torch.rand(ch, generator=g)
+        sd[name + '.num_batches_tracked'] = torch.tensor(100)
+    return sd
+
+
 def synthetic_images(batch, h, w, seed):
     g = torch.Generator().manual_seed(seed)
     img = torch.rand(batch, 1, h, w, generator=g)
@@ -74,6 +89,7 @@ CASES = {
     'superpoint_all':  (2, 96, 128, -1, 0.0, 1),          # every NMS survivor, row-major order; counts differ -> min_stack's top-k
     'superpoint_topk': (2, 120, 160, 150, 0.0, 2),        # top-k of both images
     'superpoint_thr':  (1, 64, 64, 400, 0.02, 3),         # threshold active, fewer survivors than max_keypoints: order kept
+    'superpoint_bn':   (2, 96, 128, 200, 0.0, 4),         # SuperPointNetBn: BatchNorm2d after every convolution (eval mode)
 }
 
 
@@ -81,11 +97,18 @@ def main():
     _stub_modules()
     import kornia.geometry.subpix as subpix                              # the stub module
     subpix.nms2d = nms2d
-    from models.features.superpoint.model import SuperPointNet as RefSuperPoint   # the reference, unmodified
+    from models.features.superpoint.model import SuperPointNet as RefSuperPoint, SuperPointNetBn as RefSuperPointBn   # the reference, unmodified
     out_dir = os.path.join(ROOT, 'tests', 'golden')
+    only = sys.argv[1:]
     for name, (batch, h, w, maxk, thr, seed) in CASES.items():
-        model = RefSuperPoint(max_keypoints=maxk, keypoint_threshold=thr)
-        print(name, model.load_state_dict(synthetic_superpoint_state_dict(seed), strict=True))
+        if only and name not in only:
+            continue
+        if name.endswith('_bn'):
+            model = RefSuperPointBn(max_keypoints=maxk, keypoint_threshold=thr)
+            print(name, model.load_state_dict(synthetic_superpoint_bn_state_dict(seed), strict=True))
+        else:
+            model = RefSuperPoint(max_keypoints=maxk, keypoint_threshold=thr)
+            print(name, model.load_state_dict(synthetic_superpoint_state_dict(seed), strict=True))
         model.eval()
         img = synthetic_images(batch, h, w, seed)
         fx = {'case': (batch, h, w, maxk, thr, seed), 'image': img,

@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-CASES = ['superpoint_all', 'superpoint_topk', 'superpoint_thr']
+CASES = ['superpoint_all', 'superpoint_topk', 'superpoint_thr', 'superpoint_bn']
 
 
 def _load(name):
@@ -52,27 +52,73 @@ def test_superpoint_fixture_is_self_consistent(name):
     assert (d.norm(dim=-1) - 1).abs().max() < 1e-5
 
 
+def test_superpoint_bn_fold_reproduces_the_reference_layers():
+    """SuperPointNetBn on the CPU: the weights the kernels are handed (BatchNorm folded into the convolution it follows, packed
+    [Cout, (3 ky + kx) Cin + ci]) reproduce the dense outputs of the reference's `_forward_layers` (fixture: float64 run of the
+    unmodified SuperPointNetBn) when the same schedule - conv, ReLU, max-pool, 1x1 heads, softmax, channel norm - runs in float64
+    torch.  Also: the reference's state_dict loads strictly, and the checkpoint key renaming follows model.py:151-171."""
+    import sys
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    from gen_golden_superpoint import synthetic_superpoint_bn_state_dict
+    from openglue_b200 import SuperPointNetBn
+    fx = _load('superpoint_bn')
+    batch, h, w, maxk, thr, seed = fx['case']
+    model = SuperPointNetBn(max_keypoints=maxk, keypoint_threshold=thr)
+    print(model.load_state_dict(synthetic_superpoint_bn_state_dict(seed), strict=True))
+    model.eval()
+    wts = model._weights()
+
+    def conv(x, name, relu=True):
+        wp, b = wts[name]
+        co, kk = wp.shape
+        k = 3 if kk == 9 * x.shape[1] else 1
+        wt = wp.double().reshape(co, k, k, -1).permute(0, 3, 1, 2)
+        y = F.conv2d(x, wt, b.double(), padding=k // 2)
+        return y.relu() if relu else y
+    x = fx['image'].double()
+    for i in range(4):
+        x = conv(conv(x, f'conv{i + 1}a'), f'conv{i + 1}b')
+        if i != 3:
+            x = F.max_pool2d(x, 2, 2)
+    desc = conv(conv(x, 'convDa'), 'convDb', relu=False)
+    desc = desc / desc.norm(dim=1, keepdim=True)
+    cell = conv(conv(x, 'convPa'), 'convPb', relu=False).softmax(1)[:, :-1]
+    heat = cell.permute(0, 2, 3, 1).reshape(batch, h // 8, w // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(batch, h, w)
+    # the fold is done in float64 and rounded once to float32: ~1e-7 relative per layer
+    assert float((heat - fx['heat_f64'].double()).abs().max()) <= 2e-6
+    assert float((desc - fx['desc_map_f64'].double()).abs().max()) <= 2e-6
+    sd = {'inc.conv.conv.0.weight': 0, 'inc.conv.conv.4.running_var': 1, 'down2.mpconv.1.conv.1.bias': 2, 'down3.mpconv.1.conv.3.weight': 3, 'convPa.weight': 4}
+    assert set(SuperPointNetBn.rename_weights_keys(sd)) == {'conv1a.weight', 'bn1b.running_var', 'bn3a.bias', 'conv4b.weight', 'convPa.weight'}
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('name', CASES)
 def test_superpoint_matches_reference(name, precision):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
-    from gen_golden_superpoint import synthetic_superpoint_state_dict
-    from openglue_b200 import SuperPointNet
+    from gen_golden_superpoint import synthetic_superpoint_bn_state_dict, synthetic_superpoint_state_dict
+    from openglue_b200 import SuperPointNet, SuperPointNetBn
     dev = torch.device('cuda:0')
     fx = _load(name)
     batch, h, w, maxk, thr, seed = fx['case']
-    model = SuperPointNet(max_keypoints=maxk, keypoint_threshold=thr, precision=precision)
-    model.load_state_dict(synthetic_superpoint_state_dict(seed), strict=True)           # the reference module's keys, strict
+    if name.endswith('_bn'):                                                             # the BatchNorm variant (model.py:132-199)
+        model = SuperPointNetBn(max_keypoints=maxk, keypoint_threshold=thr, precision=precision)
+        model.load_state_dict(synthetic_superpoint_bn_state_dict(seed), strict=True)
+    else:
+        model = SuperPointNet(max_keypoints=maxk, keypoint_threshold=thr, precision=precision)
+        model.load_state_dict(synthetic_superpoint_state_dict(seed), strict=True)       # the reference module's keys, strict
     model = model.to(dev).eval()
     lafs, scores, desc = model(fx['image'].to(dev))
     # dense cell probabilities -> heat map, against the reference's fp64 layers
     probs = model.last_probs
     heat = probs[..., :64].reshape(batch, h // 8, w // 8, 8, 8).permute(0, 1, 3, 2, 4).reshape(batch, h, w).cpu()
     err = float((heat.double() - fx['heat_f64'].double()).abs().max())
-    print(f'{name} {precision}: max |heat - ref64| {err:.2e}; keypoints {tuple(lafs.shape)}')
-    assert err <= 1e-5
+    ref_err = float((fx['heat_f32'].double() - fx['heat_f64'].double()).abs().max())    # the reference's own fp32 rounding on this input
+    bound = max(1e-5, 5 * ref_err)                    # (1.0e-6 .. 1.3e-6 on the plain fixtures, 3.9e-6 behind the BatchNorm scales)
+    print(f'{name} {precision}: max |heat - ref64| {err:.2e} (bound {bound:.1e}, ref32-vs-ref64 {ref_err:.1e}); keypoints {tuple(lafs.shape)}')
+    assert err <= bound
     # keypoints: identical wherever the reference's decision is decisive at 10x that error
     lafs, scores, desc = lafs.cpu(), scores.cpu(), desc.cpu()
     keep, decisive = _decisions(fx['heat_f64'].float(), 9, thr, 4, 10 * max(err, 1e-7))
