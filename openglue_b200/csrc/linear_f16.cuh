@@ -29,6 +29,12 @@
 #include <algorithm>
 #include <stdlib.h>
 
+// OG_GEMM_CONV2 (default 0 until verified on the GPU): the A converters load the whole fp32 row, hand the shared-memory slot back
+// and only then split it, with packed fp32x2 arithmetic.
+#ifndef OG_GEMM_CONV2
+#define OG_GEMM_CONV2 0
+#endif
+
 namespace og {
 
 struct F16LinearArgs {
@@ -78,6 +84,27 @@ template <int PAIR> struct Cfg {
   static constexpr int B_STAGE = 2 * B_TILE;
   static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_BYTES + B_STAGES * B_STAGE + OUT_BYTES + 1536;   // 231936 of 232448 bytes
 };
+
+__device__ __forceinline__ unsigned long long pk2(float x, float y) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+// hi = fp16(x), lo = fp16(x - hi) for a packed pair of fp32 values (the scalar form is tc::split_f16x2)
+__device__ __forceinline__ void split_f16x2_packed(unsigned long long x2, uint32_t& hi, uint32_t& lo) {
+  float x0, x1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  unsigned long long r2;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r2) : "l"(x2), "l"(pk2(f.x, f.y)));
+  float r0, r1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r2));
+  const __half2 l = __floats2half2_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 struct __align__(16) Barriers {
   uint64_t a_land[MAX_STAGES], a_free[MAX_STAGES], b_full[MAX_STAGES], b_free[MAX_STAGES], a_full[MAX_STAGES], a_empty[MAX_STAGES];
@@ -271,6 +298,33 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         mbar_wait(&bars->a_land[s], ph);
         if (warp == 8 && lane == 0) OG_TRACE_EVT(1, it);
         uint32_t hi[32], lo[32];
+#if OG_GEMM_CONV2
+        // the whole row (64 floats) goes to registers first and the smem slot is handed back BEFORE the split: a slot lives
+        // TMA latency (~2500 cycles) + the time until this arrive, and the A ring is what paces the main loop (3 slots of 32 KB;
+        // event trace profiles/r02_trace_gemm_f16_fc2_v2_two_rings.txt: one K block per ~1150 cycles against 768 of MMA work).
+        // The loads are ordered before the release-arrive by the memory model (__syncwarp orders the lanes' accesses).
+        ulonglong2 v[16];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint8_t* arow = sm_a + s * A_BYTES + j * A_SUB + trow * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[j * 8 + c] = *reinterpret_cast<const ulonglong2*>(arow + ((c ^ (trow & 7)) * 16));   // undo the 128B swizzle
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->a_free[s]);
+        {
+          const unsigned long long s2 = tcf::pk2(s_a, s_a);
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {               // packed fp32x2 scale / residual (bit-identical to the scalar form)
+            tcf::split_f16x2_packed(tcf::mul2(v[w].x, s2), hi[2 * w], lo[2 * w]);
+            tcf::split_f16x2_packed(tcf::mul2(v[w].y, s2), hi[2 * w + 1], lo[2 * w + 1]);
+          }
+        }
+        if (a.swap_halves) {
+#pragma unroll
+          for (int w = 0; w < 32; ++w) { hi[w] = __byte_perm(hi[w], 0, 0x1032); lo[w] = __byte_perm(lo[w], 0, 0x1032); }
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint8_t* arow = sm_a + s * A_BYTES + j * A_SUB + trow * 128;
@@ -287,6 +341,7 @@ __global__ void __launch_bounds__(tcf::THREADS, 1) linear_f16_kernel(const __gri
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->a_free[s]);          // this warp is done with the smem A tile: the producer may refill it
+#endif
         mbar_wait(&bars->a_empty[s], ph ^ 1);
         tc_fence_after();
         const uint32_t taddr = tmem + lane_base + COL_A + s * 64;

@@ -1,0 +1,76 @@
+#!/bin/bash
+# Round-2 visit W (15 GPU-minutes left: ONE shot): A/B of the compile-time variants of the fp16 attention kernel (early S hand-back,
+# fold before the exponentials, last team merges) and of the GEMM converter (early slot release + packed math), full GPU test
+# suite on the chosen build, smoke, launch list.  Every step under its own timeout; results land in gpurun_out/ as they come.
+cd "$GRAFT_REPO_ROOT" || exit 1
+set +e
+mkdir -p gpurun_out
+O=gpurun_out
+AB=openglue_b200/ab
+T0=$(date +%s)
+el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
+
+# 1. attention operator: parity + timing per build
+: > $O/w_ab_attention.jsonl
+for v in default early early_fold early_merger all; do
+  if [ "$v" = default ]; then L=openglue_b200/libopenglue_b200.so; else L=$AB/lib_$v.so; fi
+  OG_LIB=$L timeout 150 python scripts/ab_attention.py 2> $O/w_ab_$v.err | tail -1 >> $O/w_ab_attention.jsonl
+  el "ab_attention $v done"
+done
+cat $O/w_ab_attention.jsonl | cut -c1-600
+
+# 2. choose the fastest build whose parity is intact
+BEST=$(python - <<'P'
+import json
+best, bt = 'default', None
+for line in open('gpurun_out/w_ab_attention.jsonl'):
+    try: d = json.loads(line)
+    except Exception: continue
+    name = 'default' if d['lib'].endswith('libopenglue_b200.so') else d['lib'].split('lib_')[-1][:-3]
+    if d.get('ok') and 'ms_self_32x4x2048x2048' in d:
+        t = d['ms_self_32x4x2048x2048'] + d['ms_cross_16x4x2048x2048']
+        if name == 'default' and bt is None: bt = t
+        if bt is None or t < bt * 0.995: best, bt = name, t
+print(best)
+P
+)
+el "best attention build: $BEST"
+if [ "$BEST" = default ]; then LA=openglue_b200/libopenglue_b200.so; LC=$AB/lib_conv2.so; else LA=$AB/lib_$BEST.so; LC=$AB/lib_${BEST}_conv2.so; fi
+
+# 3. whole step (verified against the reference fixture inside bench.py): chosen attention build, + GEMM converter variant, baseline
+OG_LIB=$LA timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $O/w_bench_attn.json 2> $O/w_bench_attn.err; el "bench $LA"
+OG_LIB=$LC timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $O/w_bench_attn_conv2.json 2> $O/w_bench_attn_conv2.err; el "bench $LC"
+CHOSEN=$(python - "$LA" "$LC" <<'P'
+import json, sys
+def val(p):
+    try:
+        d = json.load(open(p)); return d['value'] if d.get('verified', {}).get('matches0_identical') else 0.0
+    except Exception: return 0.0
+a, c = val('gpurun_out/w_bench_attn.json'), val('gpurun_out/w_bench_attn_conv2.json')
+print(sys.argv[2] if c > a * 1.003 else sys.argv[1])
+P
+)
+el "chosen build: $CHOSEN"
+echo "$BEST $CHOSEN" > $O/w_chosen.txt
+python - <<'P'
+import json
+for n in ('w_bench_attn', 'w_bench_attn_conv2'):
+    try:
+        d = json.load(open(f'gpurun_out/{n}.json'))
+        print(n, round(d['value'], 1), 'pairs/s', round(d['ms_per_step'], 3), 'ms; e2e', round(d['e2e']['value'], 1), '; attn ms', round(d['roofline']['ms_per_launch'], 4),
+              'frac', round(d['roofline']['frac'], 4), '; sink ms', round(d['roofline_sinkhorn']['ms_per_launch'], 3), d['verified']['matches0_identical'], d['clocks'])
+    except Exception as e:
+        print(n, 'failed', e)
+        try: print(open(f'gpurun_out/{n}.err').read()[-600:])
+        except Exception: pass
+P
+
+# 4. the full GPU suite + smoke on the chosen build (what becomes the default)
+OG_LIB=$CHOSEN timeout 400 python -m pytest tests -m gpu -q --timeout 300 -rf 2>&1 | tail -40 > $O/w_pytest_gpu.log; tail -5 $O/w_pytest_gpu.log; el "pytest"
+OG_LIB=$CHOSEN timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1 | tee $O/w_smoke.log; el "smoke"
+
+# 5. evidence: launch list of one step, tensor-pipe activity of the attention launches (chosen build)
+OG_LIB=$CHOSEN timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 450 --csv --log-file $O/w_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-verify --cuda-graph 0 > $O/w_ncu_bench.log 2>&1; el "launch list"
+OG_LIB=$CHOSEN timeout 200 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:attention_f16t -s 16 -c 4 --csv --log-file $O/w_ncu_attention.csv python scripts/ab_attention.py > $O/w_ncu_attention.log 2>&1; el "ncu attention"
+
+el "end"
