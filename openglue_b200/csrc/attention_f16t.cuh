@@ -41,6 +41,12 @@
 #ifndef OG_ATTN_MERGER_LAST
 #define OG_ATTN_MERGER_LAST 0
 #endif
+// OG_ATTN_PAIR_BAR (default 0, experiment): the half-row maxima are exchanged between the two warps that own the same 32 rows
+// (one in each warpgroup of the team) behind a 64-thread named barrier of their own instead of the team's 256-thread barrier:
+// a pair no longer waits for the slowest of the team's eight warps on every key block.
+#ifndef OG_ATTN_PAIR_BAR
+#define OG_ATTN_PAIR_BAR 0
+#endif
 
 namespace og {
 namespace tcat {
@@ -378,7 +384,11 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
 #pragma unroll
       for (int c = 0; c < 32; c += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 1])));
       xch_t[(par * 2 + g) * 128 + trow] = mx;
+#if OG_ATTN_PAIR_BAR
+      asm volatile("bar.sync %0, 64;" ::"r"(4 + team * 4 + qd) : "memory");       // only the two warps that share these 32 rows
+#else
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+#endif
       mx = fmaxf(mx, xch_t[(par * 2 + (g ^ 1)) * 128 + trow]);
       if (warp == 0 && lane == 0) OG_TRACE_EVT(8, i);
       const float m_new = fmaxf(m_run, mx);

@@ -10,32 +10,38 @@ AB=openglue_b200/ab
 T0=$(date +%s)
 el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 
-# 1. attention operator: parity + timing per build
+# 1. attention operator: parity + timing per build.  E = early S hand-back; on top of it F = fold before the exponentials,
+#    M = last team merges, P = pair barriers for the row-maximum exchange
 : > $O/w_ab_attention.jsonl
-for v in default early early_fold early_merger all; do
-  if [ "$v" = default ]; then L=openglue_b200/libopenglue_b200.so; else L=$AB/lib_$v.so; fi
-  OG_LIB=$L timeout 150 python scripts/ab_attention.py 2> $O/w_ab_$v.err | tail -1 >> $O/w_ab_attention.jsonl
-  el "ab_attention $v done"
-done
-cat $O/w_ab_attention.jsonl | cut -c1-600
+run_ab() {
+  if [ "$1" = default ]; then L=openglue_b200/libopenglue_b200.so; else L=$AB/lib_$1.so; fi
+  OG_LIB=$L timeout 150 python scripts/ab_attention.py 2> $O/w_ab_$1.err | tail -1 >> $O/w_ab_attention.jsonl
+  el "ab_attention $1 done"
+}
+for v in default E EF EM EP; do run_ab $v; done
 
-# 2. choose the fastest build whose parity is intact
-BEST=$(python - <<'P'
-import json
-best, bt = 'default', None
-for line in open('gpurun_out/w_ab_attention.jsonl'):
+# 2. combine the additions that beat E on their own, measure the combination, keep the fastest build whose parity is intact
+PICK='
+import json, sys
+res = {}
+for line in open("gpurun_out/w_ab_attention.jsonl"):
     try: d = json.loads(line)
     except Exception: continue
-    name = 'default' if d['lib'].endswith('libopenglue_b200.so') else d['lib'].split('lib_')[-1][:-3]
-    if d.get('ok') and 'ms_self_32x4x2048x2048' in d:
-        t = d['ms_self_32x4x2048x2048'] + d['ms_cross_16x4x2048x2048']
-        if name == 'default' and bt is None: bt = t
-        if bt is None or t < bt * 0.995: best, bt = name, t
-print(best)
-P
-)
-el "best attention build: $BEST"
-if [ "$BEST" = default ]; then LA=openglue_b200/libopenglue_b200.so; LC=$AB/lib_conv2.so; else LA=$AB/lib_$BEST.so; LC=$AB/lib_${BEST}_conv2.so; fi
+    name = "default" if d["lib"].endswith("libopenglue_b200.so") else d["lib"].split("lib_")[-1][:-3]
+    if d.get("ok") and "ms_self_32x4x2048x2048" in d:
+        res[name] = d["ms_self_32x4x2048x2048"] + d["ms_cross_16x4x2048x2048"]
+if sys.argv[1] == "combo":
+    combo = "E" + "".join(x for x in "FMP" if res.get("E" + x, 1e9) < res.get("E", 0) * 0.995) if "E" in res else ""
+    print(combo if len(combo) > 2 else "")
+else:
+    print(min(res, key=res.get) if res else "default")
+'
+COMBO=$(python -c "$PICK" combo)
+if [ -n "$COMBO" ]; then run_ab $COMBO; fi
+cat $O/w_ab_attention.jsonl | cut -c1-700
+BEST=$(python -c "$PICK" best)
+el "best attention build: $BEST (combination tried: ${COMBO:-none})"
+if [ "$BEST" = default ]; then LA=openglue_b200/libopenglue_b200.so; LC=$AB/lib_c.so; else LA=$AB/lib_$BEST.so; LC=$AB/lib_${BEST}_c.so; fi
 
 # 3. whole step (verified against the reference fixture inside bench.py): chosen attention build, + GEMM converter variant, baseline
 OG_LIB=$LA timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $O/w_bench_attn.json 2> $O/w_bench_attn.err; el "bench $LA"
