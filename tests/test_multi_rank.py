@@ -108,3 +108,36 @@ def test_two_rank_loss_reduction_matches_single_process(tmp_path):
     g0, g1, _ = G.gt_matches(data['keypoints0'], data['keypoints1'], {'type': ['perspective'] * total, 'H': H})
     want = L.criterion({'gt_matches0': g0, 'gt_matches1': g1}, {'scores': O.run(sd, cfg, data, 0.2)['scores']})
     assert abs(float(got[0]) - float(want['loss'])) < 1e-5 and float(got[1]) == 0.0
+
+
+def _grad_worker(rank, world, port, out_path):
+    """Data-parallel step on CPU: every rank holds the same small module and its own gradients; after
+    sharding.all_reduce_gradients every rank holds the mean, bucketed (tiny bucket size -> several buckets, one of them oversized)."""
+    from openglue_b200.sharding import all_reduce_gradients
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.Linear(33, 5), torch.nn.Linear(5, 3))
+    net[2].bias.requires_grad_(False)                    # a parameter without a gradient is skipped
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in net.parameters():
+        if p.requires_grad:
+            p.grad = torch.randn(p.shape, generator=g)
+    mine = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+    nb = all_reduce_gradients(net.parameters(), bucket_bytes=256)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        torch.save({'buckets': nb, 'reduced': [p.grad for p in net.parameters() if p.grad is not None], 'per_rank': gathered}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average(tmp_path):
+    out = str(tmp_path / 'grads.pt')
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    assert got['buckets'] >= 3 and len(got['reduced']) == 5
+    for i, red in enumerate(got['reduced']):
+        want = (got['per_rank'][0][i] + got['per_rank'][1][i]) / 2
+        assert torch.allclose(red, want, rtol=0, atol=1e-7)
