@@ -134,7 +134,7 @@ def test_superpoint_matches_reference(name, precision):
             if (x, y) in ours:
                 i = ours[(x, y)]
                 matched += 1
-                assert abs(float(scores[b, i]) - float(ref_scores[b, j])) <= 1e-5
+                assert abs(float(scores[b, i]) - float(ref_scores[b, j])) <= bound + ref_err    # the fixture's scores are the reference's fp32 run
                 assert (desc[b, i] - ref_desc[b, j]).abs().max() <= 1e-4
             else:
                 assert not all_decisive, (b, x, y)
