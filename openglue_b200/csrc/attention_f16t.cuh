@@ -39,13 +39,13 @@
 // With the merge fixed on team 0 and an even block count, team 0 waited half a cycle for team 1's last block, merged (~2500
 // cycles) and only then turned to a block whose logits had been ready all along (~6000 cycles per tile boundary in the trace).
 #ifndef OG_ATTN_MERGER_LAST
-#define OG_ATTN_MERGER_LAST 0
+#define OG_ATTN_MERGER_LAST 1
 #endif
 // OG_ATTN_PAIR_BAR (default 0, experiment): the half-row maxima are exchanged between the two warps that own the same 32 rows
 // (one in each warpgroup of the team) behind a 64-thread named barrier of their own instead of the team's 256-thread barrier:
 // a pair no longer waits for the slowest of the team's eight warps on every key block.
 #ifndef OG_ATTN_PAIR_BAR
-#define OG_ATTN_PAIR_BAR 0
+#define OG_ATTN_PAIR_BAR 1
 #endif
 
 namespace og {
