@@ -225,7 +225,9 @@ def time_oracle(workload, cfg, n, m, reps):
     procs = []
     t0 = time.perf_counter()
     for sl in slices:
-        cmd = [sys.executable, os.path.abspath(__file__), '--cpu-worker', workload, str(max(2, reps)), str(per), ','.join(map(str, sl))]
+        # one warm-up + ONE timed pair per process: with every core busy a pair takes ~30 s on the GPU box's host (memory-bound), and
+        # this leg only has to show that more processes do not beat the single pinned one (visit Y: the default run took 200 s)
+        cmd = [sys.executable, os.path.abspath(__file__), '--cpu-worker', workload, '1', str(per), ','.join(map(str, sl))]
         env = dict(os.environ, OMP_NUM_THREADS=str(per), MKL_NUM_THREADS=str(per))
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env))
     rates = []
