@@ -34,7 +34,7 @@
 #ifndef OG_ATTN_FOLD_EARLY
 #define OG_ATTN_FOLD_EARLY 0
 #endif
-// OG_ATTN_MERGER_LAST (default 0, experiment): the team that owns a tile's LAST key block merges and stores the tile; the other
+// OG_ATTN_MERGER_LAST (default 1; kernel template parameter SWAP, chosen per launch: see attention_f16t_launch_t): the team that owns a tile's LAST key block merges and stores the tile; the other
 // team deposits its partial result (bar.arrive, no wait) and starts the next tile's first block, which is the earlier one.
 // With the merge fixed on team 0 and an even block count, team 0 waited half a cycle for team 1's last block, merged (~2500
 // cycles) and only then turned to a block whose logits had been ready all along (~6000 cycles per tile boundary in the trace).
@@ -92,7 +92,7 @@ __device__ __forceinline__ unsigned long long fsub2(unsigned long long a, unsign
 }
 }  // namespace tcat
 
-template <int CG>
+template <int CG, int SWAP>
 __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const __grid_constant__ CUtensorMap map_khi,
                                                                           const __grid_constant__ CUtensorMap map_klo,
                                                                           const __grid_constant__ CUtensorMap map_vhi,
@@ -458,11 +458,7 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
 
     // ---- merge the two teams' partial results of this tile (depositor -> shared memory -> merger), normalise, store
     const int tp2 = nt & 1;
-#if OG_ATTN_MERGER_LAST
-    const int merger = (it0 + nblk - 1) & 1;          // the team that finishes the tile LAST merges; the other one deposits and moves on
-#else
-    const int merger = 0;
-#endif
+    const int merger = SWAP ? ((it0 + nblk - 1) & 1) : 0;     // SWAP: the team that finishes the tile LAST merges; the other one deposits and moves on
     float* lm_t = lm + tp2 * (2 * 2 * 128 * 2);
     reinterpret_cast<float2*>(lm_t)[(team * 2 + g) * 128 + trow] = make_float2(mc_run, l_run);
     if (team != merger) {
@@ -470,16 +466,12 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
 #pragma unroll
       for (int c = 0; c < 16; ++c) { float x, y; unpack2(acc2[c], x, y); mr[2 * c] = x; mr[2 * c + 1] = y; }
     }
-#if OG_ATTN_MERGER_LAST
-    if (team != merger) {                            // producer side of the named barrier: no wait (PTX bar.arrive / bar.sync pattern)
+    if (SWAP && team != merger) {                    // producer side of the named barrier: no wait (PTX bar.arrive / bar.sync pattern)
       __threadfence_block();
       asm volatile("bar.arrive 3, 512;" ::: "memory");
     } else {
       asm volatile("bar.sync 3, 512;" ::: "memory");
     }
-#else
-    asm volatile("bar.sync 3, 512;" ::: "memory");
-#endif
     if (team == merger) {
       const float2* lmv = reinterpret_cast<const float2*>(lm_t);
       const float2 a0 = lmv[(team * 2 + (g ^ 1)) * 128 + trow], b0 = lmv[((team ^ 1) * 2 + 0) * 128 + trow], b1 = lmv[((team ^ 1) * 2 + 1) * 128 + trow];
@@ -527,8 +519,8 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
   if (warp == 17) { tc_fence_after(); if (CG == 2) tmem_dealloc_pair<tcat::TMEM_COLS>(tmem); else tmem_dealloc<tcat::TMEM_COLS>(tmem); }
 }
 
-template <int CG>
-inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
+template <int CG, int SWAP>
+inline int attention_f16t_launch_ts(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
                                    const __half* vthi, const __half* vtlo, int64_t ldvt, cudaStream_t stream) {
   using namespace tcat;
   CUtensorMap mkh, mkl, mvh, mvl;
@@ -539,13 +531,13 @@ inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   if ((rc = tc::make_tmap_2d_f16(&mvl, vtlo, (uint64_t)a.batch * a.d, (uint64_t)a.nk, (uint64_t)ldvt, DH / CG)) != OG_OK) return rc;
   static DeviceFlags attr_set;
   if (attr_set.once()) {
-    OG_CUDA(cudaFuncSetAttribute(attention_f16t_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<CG>()));
+    OG_CUDA(cudaFuncSetAttribute(attention_f16t_kernel<CG, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<CG>()));
   }
   {  // the register hand-over only works if the compiled register count gives the CTA the pool the two setmaxnreg values add up to
     static int regs_ok = -1;
     if (regs_ok < 0) {
       cudaFuncAttributes fa;
-      OG_CUDA(cudaFuncGetAttributes(&fa, attention_f16t_kernel<CG>));
+      OG_CUDA(cudaFuncGetAttributes(&fa, attention_f16t_kernel<CG, SWAP>));
       regs_ok = (fa.numRegs * THREADS >= 512 * REGS_SOFTMAX + 128 * REGS_PRODUCER) ? 1 : 0;
     }
     if (!regs_ok) return fail(OG_EUNSUPPORTED, "attention_f16t: register pool too small for the setmaxnreg split (rebuild)");
@@ -565,9 +557,23 @@ inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc,
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = tc::pdl_mode() ? 2 : 1;
-  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_f16t_kernel<CG>, mkh, mkl, mvh, mvl, ap, sc));
+  OG_CUDA(cudaLaunchKernelEx(&cfg, attention_f16t_kernel<CG, SWAP>, mkh, mkl, mvh, mvl, ap, sc));
   launch_counter()++;
   return OG_OK;
+}
+
+// The role swap at the end of a tile (OG_ATTN_MERGER_LAST) pairs a waiting `bar.sync` with a non-waiting `bar.arrive` on one named
+// barrier, which is only sound while the depositing team cannot reach the NEXT tile's barrier before the merging team has reached
+// this tile's.  With at least four key blocks per tile that is a hard dependency (the depositor's third block of the next tile needs
+// a QK^T that is issued, in order, behind one that waits for the merger's first block of that tile); with one to three blocks it
+// would rest on timing alone (the depositor's chain is the merger's plus one QK^T round trip).  Short sequences therefore run the
+// symmetric form: team 0 merges, both teams wait.
+template <int CG>
+inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
+                                   const __half* vthi, const __half* vtlo, int64_t ldvt, cudaStream_t stream) {
+  const int nblk = (a.nk + tcat::BNK - 1) / tcat::BNK;
+  if (OG_ATTN_MERGER_LAST && nblk >= 4) return attention_f16t_launch_ts<CG, 1>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  return attention_f16t_launch_ts<CG, 0>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
 }
 
 }  // namespace og
