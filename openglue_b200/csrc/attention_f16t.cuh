@@ -563,16 +563,17 @@ inline int attention_f16t_launch_ts(const TcAttnArgs& a, const F16AttnScales& sc
 }
 
 // The role swap at the end of a tile (OG_ATTN_MERGER_LAST) pairs a waiting `bar.sync` with a non-waiting `bar.arrive` on one named
-// barrier, which is only sound while the depositing team cannot reach the NEXT tile's barrier before the merging team has reached
-// this tile's.  With at least four key blocks per tile that is a hard dependency (the depositor's third block of the next tile needs
-// a QK^T that is issued, in order, behind one that waits for the merger's first block of that tile); with one to three blocks it
-// would rest on timing alone (the depositor's chain is the merger's plus one QK^T round trip).  Short sequences therefore run the
-// symmetric form: team 0 merges, both teams wait.
+// barrier, which is only sound while the team that deposits for tile t+1 cannot reach that barrier before the team that merges tile t
+// has reached tile t's.  With an odd block count the two are the same team (program order).  With an even count the depositor's last
+// block of tile t+1 has index nblk - 2 and the merger's first block there has index 1; QK^T is issued in block order and QK^T of block
+// 3 waits for the merger's P of block 1, which it writes after tile t's barrier - so from nblk - 2 >= 4 on the order is a hard
+// dependency, while below that it would rest on timing alone (the depositor's chain is the merger's plus at least one QK^T round
+// trip).  Sequences of fewer than six key blocks therefore run the symmetric form: team 0 merges, both teams wait.
 template <int CG>
 inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
                                    const __half* vthi, const __half* vtlo, int64_t ldvt, cudaStream_t stream) {
   const int nblk = (a.nk + tcat::BNK - 1) / tcat::BNK;
-  if (OG_ATTN_MERGER_LAST && nblk >= 4) return attention_f16t_launch_ts<CG, 1>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
+  if (OG_ATTN_MERGER_LAST && nblk >= 6) return attention_f16t_launch_ts<CG, 1>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
   return attention_f16t_launch_ts<CG, 0>(a, sc, khi, klo, ldk, vthi, vtlo, ldvt, stream);
 }
 
