@@ -193,7 +193,9 @@ int og_linear_tc_fwd(const og_linear_args* args, const float* Whi, const float* 
  * Replaces softmax_attention (models/superglue/attention.py:8-19) inside
  * MultiheadAttention.forward (attention_gnn.py:22-32); the N x M probabilities are never
  * materialised.  q [batch][nq, *] row stride ldq; k, v [batch][nk, *]; heads are contiguous
- * channel blocks of width Dh = d / H.                                                        */
+ * channel blocks of width Dh = d / H.  Raw fp32 operands: this entry point always runs the exact
+ * fp32 kernel whatever `precision` says; the tensor-core forms take operands that the projection
+ * GEMMs have already split (og_attention_tc_fwd, og_attention_f16_fwd).                        */
 int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq,
                      const float* k, int64_t ldk, int64_t stridek,
                      const float* v, int64_t ldv, int64_t stridev,

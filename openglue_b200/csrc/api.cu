@@ -182,10 +182,8 @@ static int linear_dispatch(const og_linear_args& a, int precision, cudaStream_t 
   return linear_simt_launch(a, s);
 }
 
-static int attention_dispatch(const AttnArgs& a, int head_dim, int precision, cudaStream_t s) {
-  (void)precision;
-  return attention_simt_launch(a, head_dim, s);
-}
+// exact fp32 attention (CUDA cores); the tensor-core forms take pre-split operands and have their own entry points
+static int attention_fp32(const AttnArgs& a, int head_dim, cudaStream_t s) { return attention_simt_launch(a, head_dim, s); }
 
 }  // namespace og
 
@@ -321,9 +319,10 @@ int og_attention_fwd(const float* q, int64_t ldq, int64_t strideq, const float* 
                      int batch, int nq, int nk, int num_heads, int head_dim, int precision, void* stream) {
   OG_CHECK_ARG(q && k && v && out, "attention: null pointer");
   OG_CHECK_ARG(batch > 0 && nq > 0 && nk > 0 && num_heads > 0 && head_dim > 0, "attention: bad sizes");
+  (void)precision;                                   // raw fp32 operands: always the exact kernel (see the header)
   AttnArgs a{q, ldq, strideq, k, ldk, stridek, v, ldv, stridev, out, ldo, strideo, batch, nq, nk, num_heads,
              (float)pow((double)head_dim, -0.5)};
-  return attention_dispatch(a, head_dim, precision, (cudaStream_t)stream);
+  return attention_fp32(a, head_dim, (cudaStream_t)stream);
 }
 
 int og_attention_tc_fwd(const float* q, int64_t ldq, int64_t strideq, const float* khi, const float* klo, int64_t ldk,
@@ -692,7 +691,7 @@ static int forward_impl(const og_config* cfg, const float* Wp, const float* Whi,
                w.qkv + (int64_t)krow0 * 3 * d + d, 3 * d, (int64_t)nk * 3 * d,
                w.qkv + (int64_t)krow0 * 3 * d + 2 * d, 3 * d, (int64_t)nk * 3 * d,
                w.o + (int64_t)qrow0 * d, d, (int64_t)nq * d, batch, nq, nk, H, (float)pow((double)dh, -0.5)};
-    return attention_dispatch(a, dh, prec, st);
+    return attention_fp32(a, dh, st);
   };
   auto mlp = [&](int l, int row0, int rows) -> int {
     // x <- x + W2 . relu(W1 . [x ; o] + b1) + b2     (out_proj and BN folded into W1 / W2 on the host)
