@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(tcat::THREADS, 1) attention_f16t_kernel(const 
     uint64_t* const bar_p = &bars->p_full[team];
     uint64_t* const bar_of = &bars->o_full[team];
     uint64_t* const bar_oe = &bars->o_empty[team];
+#if !OG_ATTN_PAIR_BAR
     const int bar_id = 1 + team;
+#endif
 
     auto load_q = [&](const TilePos& p) {            // cp.async: lands during the tile
       const int r_in = lane / LPR, ch = lane % LPR;
