@@ -118,3 +118,36 @@ def test_oracle_equals_staged_reference():
         got = O.run(sd, cfg, data, 0.2)
         for key in ('scores', 'context_descriptors0', 'context_descriptors1'):
             assert torch.equal(got[key], want[key]), key
+
+
+def test_label_and_loss_oracles_equal_staged_reference():
+    """The two neighbouring steps on fresh seeds, live against the staged reference (oracle/_ref): ground-truth matches from a
+    homography (models/gt_matches_generation.py:17-93 vs oracle/gt_matches_oracle.py) and the matching loss
+    (utils/losses.py:7-53 vs oracle/loss_oracle.py), both bit for bit."""
+    from oracle.build_ref import import_reference
+    ref = import_reference()
+    if ref is None:
+        pytest.skip('oracle/_ref is not staged (run `python oracle/build_ref.py` where /root/reference exists)')
+    from oracle import gt_matches_oracle as G
+    from oracle import loss_oracle as L
+    _, ref_criterion, ref_generate = ref
+    for seed, (b, n, m) in [(21, (2, 60, 45)), (22, (3, 33, 80))]:
+        g = torch.Generator().manual_seed(seed)
+        k0 = torch.rand(b, n, 2, generator=g) * torch.tensor([640.0, 480.0])
+        H = torch.tensor([[0.9, 0.05, 20.0], [-0.04, 0.95, 12.0], [1e-5, 2e-5, 1.0]]).repeat(b, 1, 1)
+        k0h = torch.cat([k0, torch.ones(b, n, 1)], -1) @ H.transpose(1, 2)
+        k0w = k0h[..., :2] / k0h[..., 2:]
+        npl = min(n, m // 2)
+        k1 = torch.cat([k0w[:, :npl] + 0.3 * torch.randn(b, npl, 2, generator=g),            # planted correspondences + clutter
+                        torch.rand(b, m - npl, 2, generator=g) * torch.tensor([640.0, 480.0])], 1)
+        tf = {'type': ['perspective'] * b, 'H': H}
+        feat = lambda k: {'keypoints': k, 'local_descriptors': torch.zeros(b, k.shape[1], 4), 'side_info': torch.zeros(b, k.shape[1], 1)}
+        _, y_true = ref_generate({'transformation': tf}, feat(k0), feat(k1), positive_threshold=3.0, negative_threshold=5.0)
+        g0, g1, _ = G.gt_matches(k0, k1, tf)
+        assert torch.equal(g0, y_true['gt_matches0']) and torch.equal(g1, y_true['gt_matches1'])
+        assert int((g0 >= 0).sum()) > 0
+        scores = torch.log_softmax(torch.randn(b, n + 1, m + 1, generator=g), dim=-1)
+        y_pred = {'scores': scores, 'context_descriptors0': torch.randn(b, 8, n, generator=g), 'context_descriptors1': torch.randn(b, 8, m, generator=g)}
+        want = ref_criterion(y_true, y_pred, margin=None)
+        got = L.criterion({'gt_matches0': g0, 'gt_matches1': g1}, {'scores': scores})
+        assert torch.equal(got['loss'], want['loss']) and float(got['metric_loss']) == float(want['metric_loss']) == 0.0
