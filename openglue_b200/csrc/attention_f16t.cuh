@@ -565,12 +565,12 @@ inline int attention_f16t_launch_ts(const TcAttnArgs& a, const F16AttnScales& sc
 }
 
 // The role swap at the end of a tile (OG_ATTN_MERGER_LAST) pairs a waiting `bar.sync` with a non-waiting `bar.arrive` on one named
-// barrier, which is only sound while the team that deposits for tile t+1 cannot reach that barrier before the team that merges tile t
-// has reached tile t's.  With an odd block count the two are the same team (program order).  With an even count the depositor's last
-// block of tile t+1 has index nblk - 2 and the merger's first block there has index 1; QK^T is issued in block order and QK^T of block
-// 3 waits for the merger's P of block 1, which it writes after tile t's barrier - so from nblk - 2 >= 4 on the order is a hard
-// dependency, while below that it would rest on timing alone (the depositor's chain is the merger's plus at least one QK^T round
-// trip).  Sequences of fewer than six key blocks therefore run the symmetric form: team 0 merges, both teams wait.
+// barrier, which is only sound while no team can reach the barrier for tile t+1 before the other team has reached it for tile t (one
+// generation would then be completed by two arrivals of the same team).  QK^T is issued in global block order and QK^T(g) waits for
+// P(g-2): a team's third block of tile t+1 therefore sits behind a QK^T that waits for the OTHER team's first P of tile t+1, which
+// that team writes after tile t's barrier - from five key blocks per tile on the order is a hard dependency, below that it would rest
+// on timing alone (tests/test_attention_protocol_model.py explores every interleaving of this protocol).  Sequences of fewer than six
+// key blocks therefore run the symmetric form: team 0 merges, both teams wait.
 template <int CG>
 inline int attention_f16t_launch_t(const TcAttnArgs& a, const F16AttnScales& sc, const __half* khi, const __half* klo, int64_t ldk,
                                    const __half* vthi, const __half* vtlo, int64_t ldvt, cudaStream_t stream) {
