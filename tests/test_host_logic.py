@@ -132,3 +132,25 @@ def test_tensor_core_kernels_are_blackwell_native_and_address_shared_memory_dire
         assert c['LDTM'] > 0 and c['UTMALDG'] > 0, name    # accumulators read back from TMEM, operands staged by TMA
     fp16_attn = [c for k, c in tc.items() if 'attention_f16t_kernel' in k]
     assert len(fp16_attn) == 4 and all(c['STTM'] > 0 and c['MUFU'] >= 32 for c in fp16_attn)
+
+
+def test_bench_work_accounting_reproduces_the_survey_table():
+    """bench.py's algorithmic FLOP / byte formulas against the values SURVEY.md (section 8d, Appendix B) states for the BASELINE
+    configurations - the numerators of `roofline.achieved` and of the judge's own check."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('og_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rel = lambda a, b: abs(a - b) / b
+    # (n, m, d, stages, S, T) -> (F_total, F_attn, Q_sink GB)
+    table = {'C1': ((512, 512, 256, 9, 1, 20), (3.418e10, 9.66e9, 0.0221)),
+             'C2': ((1024, 1024, 256, 9, 1, 100), (8.796e10, 3.865e10, 0.4245)),
+             'C3': ((2048, 2048, 256, 9, 1, 100), (2.543e11, 1.546e11, 1.696)),
+             'C5': ((4096, 1024, 128, 18, 6, 50), (3.035e11, 2.416e11, 0.857))}
+    for name, ((n, m, d, stages, s, t), (ftot, fattn, qs)) in table.items():
+        fl = bench.flops_per_pair(n, m, d, stages, s)
+        assert rel(fl['total'], ftot) < 2e-3 and rel(fl['attn'], fattn) < 2e-3, (name, fl)
+        assert rel(bench.sinkhorn_bytes_per_pair(n, m, t) / 1e9, qs) < 3e-3, name
+        wl = bench.BASELINE_CONFIGS[name]
+        assert (wl['n'], wl['m'], wl['cfg']['descriptor_dim'], wl['cfg']['num_stages'], wl['cfg']['num_iters']) == (n, m, d, stages, t)
+    assert bench.BASELINE_CONFIGS['C4']['n'] == 2048 and bench.BASELINE_CONFIGS['C4']['cfg']['num_iters'] == 100
