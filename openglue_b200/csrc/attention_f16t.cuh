@@ -21,15 +21,16 @@
 #include <stdlib.h>
 #include <algorithm>
 
-// OG_ATTN_EARLY_S (default 0 until verified on the GPU): the QK^T issuer waits for "S_{i-2} is in the team's registers" (s_free, arrived right after the
+// OG_ATTN_EARLY_S (default 0: parity-clean on B200 but measured SLOWER, 0.336 -> 0.344 ms per self layer): the QK^T issuer waits for "S_{i-2} is in the team's registers" (s_free, arrived right after the
 // tcgen05.ld of the logits) instead of "P_{i-2} has been written" (p_full, ~1300 cycles later).  The event trace of the p_full form
 // (profiles/r02_trace_attention_f16_two_teams.txt) shows QK^T_{i+2} issued the moment P_i is handed over and its logits seen ~830
 // cycles after that: a team's cycle was softmax (1650) + MMA round trip (830) per two key blocks.  S and P occupy disjoint TMEM
-// columns, so the next QK^T of a buffer only has to wait for the load.
+// columns, so the next QK^T of a buffer only has to wait for the load.  The wait for S disappears - and the kernel slows down,
+// presumably because the teams are no longer held in anti-phase by the issue order (profiles/README.md, finding 8).
 #ifndef OG_ATTN_EARLY_S
 #define OG_ATTN_EARLY_S 0
 #endif
-// OG_ATTN_FOLD_EARLY (default 0, experiment): fold O_{i-2} into the registers BEFORE the exponentials of block i (in four
+// OG_ATTN_FOLD_EARLY (default 0: measured neutral): fold O_{i-2} into the registers BEFORE the exponentials of block i (in four
 // 8-column loads: the logits are live) instead of after P_i has been handed over, so that P.V_i never waits for the fold.
 #ifndef OG_ATTN_FOLD_EARLY
 #define OG_ATTN_FOLD_EARLY 0
@@ -37,11 +38,11 @@
 // OG_ATTN_MERGER_LAST (default 1; kernel template parameter SWAP, chosen per launch: see attention_f16t_launch_t): the team that owns a tile's LAST key block merges and stores the tile; the other
 // team deposits its partial result (bar.arrive, no wait) and starts the next tile's first block, which is the earlier one.
 // With the merge fixed on team 0 and an even block count, team 0 waited half a cycle for team 1's last block, merged (~2500
-// cycles) and only then turned to a block whose logits had been ready all along (~6000 cycles per tile boundary in the trace).
+// cycles) and only then turned to a block whose logits had been ready all along (~6000 cycles per tile boundary in the trace).  Measured -1.5 %.
 #ifndef OG_ATTN_MERGER_LAST
 #define OG_ATTN_MERGER_LAST 1
 #endif
-// OG_ATTN_PAIR_BAR (default 0, experiment): the half-row maxima are exchanged between the two warps that own the same 32 rows
+// OG_ATTN_PAIR_BAR (default 1: -0.4 %): the half-row maxima are exchanged between the two warps that own the same 32 rows
 // (one in each warpgroup of the team) behind a 64-thread named barrier of their own instead of the team's 256-thread barrier:
 // a pair no longer waits for the slowest of the team's eight warps on every key block.
 #ifndef OG_ATTN_PAIR_BAR
